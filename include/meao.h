@@ -1,0 +1,210 @@
+/*
+ * meao.h -- C ABI of libmeao.so: the B200-native multi-scale SSAO pipeline that stands in for
+ * the compute path of keijiro/MiniEngineAO's AmbientOcclusion component.
+ *
+ * The reference has no FFI seam: its boundary is the set of CommandBuffer calls
+ * AmbientOcclusion.cs makes against four ComputeShader assets.  Each entry point below names
+ * the reference interface it replaces (paths relative to /root/reference/Assets/MiniEngineAO/).
+ * The C# P/Invoke binding a maintainer would add is host/AmbientOcclusionNative.cs and is
+ * described in INTEGRATION.md.
+ *
+ * Conventions: plain C types only; every call returns 0 on success or a negative MeaoStatus;
+ * meao_last_error() gives the text.  A context is owned by one thread at a time (the reference
+ * records on Unity's main thread and replays on one render thread); distinct contexts are
+ * independent.  The caller owns the depth input and the AO output memory; the context owns the
+ * 16 intermediate buffers (LinearDepth, LowDepth1-4, Occlusion1-4, Combined1-3; the four
+ * TiledDepth atlases are virtual).
+ * There is NO CPU fallback: every compute entry point fails with MEAO_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef MEAO_H
+#define MEAO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define MEAO_ABI_VERSION 1
+
+typedef struct MeaoCtx MeaoCtx;
+
+typedef enum {
+    MEAO_OK = 0,
+    MEAO_ERR_INVALID = -1,      /* bad argument / call order */
+    MEAO_ERR_CUDA = -2,         /* CUDA runtime or driver error, or no usable device */
+    MEAO_ERR_UNSUPPORTED = -3,  /* e.g. halo deeper than the neighbouring band */
+    MEAO_ERR_NOMEM = -4
+} MeaoStatus;
+
+/* AmbientOcclusion.cs:20-68 -- the serialized parameter surface, same names, ranges, defaults. */
+typedef struct {
+    float noise_filter_tolerance;   /* Range(-8, 0)    default 0      AO.cs:20-26 */
+    float blur_tolerance;           /* Range(-8, -1)   default -4.6   AO.cs:28-34 */
+    float upsample_tolerance;       /* Range(-12, -1)  default -12    AO.cs:36-42 */
+    float thickness_modifier;       /* Range(1, 10)    default 1      AO.cs:44-50 */
+    float intensity;                /* Range(0, 2)     default 1      AO.cs:52-58 */
+    int32_t debug;                  /* Range(0, 17)    default 0      AO.cs:60    (carried; selects nothing on the compute path) */
+    int32_t ambient_only;           /* default 1       AO.cs:62-68   (carried; composite is out of scope) */
+} MeaoParams;
+
+/* Camera inputs of the CPU-side constant math: AO.cs:561-573. */
+typedef struct {
+    float near_clip;        /* camera.nearClipPlane                         AO.cs:563 */
+    float far_clip;         /* camera.farClipPlane                          AO.cs:563 */
+    float tan_half_fov_h;   /* 1 / camera.projectionMatrix[0,0]             AO.cs:570-573 */
+    int32_t reversed_z;     /* SystemInfo.usesReversedZBuffer (D3D11/12: 1) AO.cs:564, Downsample1.compute:41-45 */
+} MeaoCamera;
+
+typedef struct {
+    int32_t device;         /* CUDA device ordinal; < 0 = host-side PLANNING context only (constants, geometry,
+                               band / halo row ranges) -- every compute call on it fails with MEAO_ERR_CUDA */
+    uint32_t flags;         /* MEAO_FLAG_* */
+} MeaoDeviceCfg;
+
+#define MEAO_FLAG_NONE        0u
+#define MEAO_FLAG_NO_GRAPH    1u   /* launch the kernels on the stream instead of replaying the captured CUDA graph */
+
+typedef enum {
+    MEAO_DEPTH_RAW_F32 = 0,     /* camera depth, linearised by Downsample1.compute:37-48 (reference behaviour) */
+    MEAO_DEPTH_LINEAR_F32 = 1   /* already-linear depth (Linearize becomes the identity; not in the reference) */
+} MeaoDepthKind;
+
+/* Debug buffer ids, numbering of AmbientOcclusion.cs:787-808. */
+typedef enum {
+    MEAO_BUF_LINEAR_DEPTH = 1,                                  /* L0, f16 */
+    MEAO_BUF_LOW_DEPTH1 = 2, MEAO_BUF_LOW_DEPTH2 = 3,           /* L1..L4, f32 */
+    MEAO_BUF_LOW_DEPTH3 = 4, MEAO_BUF_LOW_DEPTH4 = 5,
+    MEAO_BUF_TILED_DEPTH1 = 6, MEAO_BUF_TILED_DEPTH2 = 7,       /* L3..L6 x 16 slices, f16 */
+    MEAO_BUF_TILED_DEPTH3 = 8, MEAO_BUF_TILED_DEPTH4 = 9,
+    MEAO_BUF_OCCLUSION1 = 10, MEAO_BUF_OCCLUSION2 = 11,         /* L1..L4, unorm8 */
+    MEAO_BUF_OCCLUSION3 = 12, MEAO_BUF_OCCLUSION4 = 13,
+    MEAO_BUF_COMBINED1 = 14, MEAO_BUF_COMBINED2 = 15, MEAO_BUF_COMBINED3 = 16,   /* L1..L3, unorm8 */
+    MEAO_BUF_AMBIENT_OCCLUSION = 17                             /* L0, unorm8 */
+} MeaoBufferId;
+
+typedef struct {
+    int32_t width, height, slices;  /* reference texture dimensions (AO.cs:276-281; slices = 16 when tiled, AO.cs:154) */
+    int32_t elem_bytes;             /* 1 = unorm8, 2 = f16 bits, 4 = f32  (AO.cs:262-273) */
+} MeaoBufferDesc;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* replaces: component construction + DoLazyInitialization (AO.cs:440-494). */
+int meao_create(const MeaoDeviceCfg *cfg, MeaoCtx **out_ctx);
+/* replaces: OnDestroy (AO.cs:357-381). */
+void meao_destroy(MeaoCtx *ctx);
+const char *meao_last_error(const MeaoCtx *ctx);   /* ctx may be NULL: error of the last failed meao_create on this thread */
+int meao_abi_version(void);
+
+/* ---- parameters (plan inputs) ---------------------------------------------------------------- */
+/* replaces: the property setters AO.cs:22-66.  Marks the plan dirty iff a value changed
+ * (CheckPropertiesChanged, AO.cs:104-113); returns 1 if the plan was dirtied, 0 if not. */
+int meao_set_params(MeaoCtx *ctx, const MeaoParams *params);
+int meao_get_params(const MeaoCtx *ctx, MeaoParams *out);
+void meao_default_params(MeaoParams *out);          /* AO.cs:20-68 defaults */
+/* replaces: CalculateZBufferParams / CalculateTanHalfFovHeight inputs (AO.cs:561-573). */
+int meao_set_camera(MeaoCtx *ctx, const MeaoCamera *camera);
+/* replaces: RTHandle.SetBaseDimensions + AllocateNow + the rebuild it triggers (AO.cs:338-341, 501-506).
+ * Allocates the intermediates for width x height.  Returns 1 if dimensions changed, 0 if not. */
+int meao_resize(MeaoCtx *ctx, int32_t width, int32_t height);
+
+/* ---- the frame ------------------------------------------------------------------------------- */
+/* replaces: replay of the "SSAO" command buffer, steps 1-10 of RebuildCommandBuffers (AO.cs:511-531):
+ * Downsample1+2, Render x4, Upsample x4.  depth: device pointer, width*height f32, rows contiguous
+ * (row pitch = width*4).  ao_out: device pointer, width*height bytes (R8, AO.cs:475).
+ * stream: a cudaStream_t (NULL = the context's own stream).  Asynchronous.  Re-plans first if dirty
+ * (LateUpdate, AO.cs:329-350). */
+int meao_render(MeaoCtx *ctx, const void *depth_dev, int32_t depth_kind, void *ao_out_dev, void *stream);
+/* Same with HOST buffers: H2D copy of depth, the ten passes, D2H copy of the AO texture, then a
+ * stream synchronise.  Use meao_host_alloc for pinned memory. */
+int meao_render_host(MeaoCtx *ctx, const float *depth_host, int32_t depth_kind, uint8_t *ao_out_host);
+int meao_synchronize(MeaoCtx *ctx);
+void *meao_host_alloc(size_t bytes);                /* cudaHostAlloc; NULL on failure */
+void meao_host_free(void *p);
+
+/* ---- per-stage entry points (stage parity; mirror the three Push*Commands recorders) ----------- */
+/* replaces: PushDownsampleCommands (AO.cs:604-658) -> LinearDepth, LowDepth1..4 (+ virtual TiledDepth1..4) */
+int meao_stage_downsample(MeaoCtx *ctx, const void *depth_dev, int32_t depth_kind, void *stream);
+/* replaces: PushRenderCommands (AO.cs:660-748) for TiledDepth<level> -> Occlusion<level>, level 1..4 */
+int meao_stage_render(MeaoCtx *ctx, int32_t level, void *stream);
+/* replaces: PushUpsampleCommands (AO.cs:750-785) with the wiring of AO.cs:528-531; lo_level 4..1.
+ * lo_level == 1 writes the final AO into ao_out_dev (or the context's own result buffer if NULL). */
+int meao_stage_upsample(MeaoCtx *ctx, int32_t lo_level, void *ao_out_dev, void *stream);
+
+/* ---- buffers (debug views, AO.cs:787-820) ------------------------------------------------------ */
+int meao_buffer_desc(const MeaoCtx *ctx, int32_t buffer_id, MeaoBufferDesc *out);
+/* Copies buffer <id> to host in the REFERENCE layout (tightly packed rows; tiled = [16][h][w]) and
+ * native storage type (f16 bits / f32 / unorm8 codes).  Synchronises the context stream.
+ * The TiledDepth views are synthesised from LowDepth<k> exactly as Downsample1/2 would have
+ * written them (including the padding texels). */
+int meao_get_buffer(MeaoCtx *ctx, int32_t buffer_id, void *host_out, size_t host_bytes);
+/* Test hook: overwrite an intermediate (ids 1-5, 10-17) from host data in the same format. */
+int meao_set_buffer(MeaoCtx *ctx, int32_t buffer_id, const void *host_in, size_t host_bytes);
+
+/* ---- CPU-side constants, exposed so they can be checked against the reference math ------------- */
+/* out[0..11] gInvThicknessTable, out[12..23] gSampleWeightTable, out[24..25] gInvSliceDimension,
+ * out[26] gRejectFadeoff, out[27] gIntensity            (AO.cs:678-734) */
+int meao_render_constants(MeaoCtx *ctx, int32_t level, float out28[28]);
+/* out[0..1] InvLowResolution, out[2..3] InvHighResolution, out[4] NoiseFilterStrength, out[5] StepSize,
+ * out[6] kBlurTolerance, out[7] kUpsampleTolerance       (AO.cs:760-771) */
+int meao_upsample_constants(MeaoCtx *ctx, int32_t lo_level, float out8[8]);
+/* out[0..3] ZBufferParams (AO.cs:561-568) */
+int meao_zbuffer_params(MeaoCtx *ctx, float out4[4]);
+
+/* ---- row-band partitioning of one frame over several GPUs (new capability) -------- */
+/* This context computes output rows [row0, row1) of the width x height frame set by meao_resize
+ * (global coordinates everywhere; image-edge semantics only at the true top/bottom).
+ * row0/row1 must be multiples of 16 except row1 == height.  prev_row0 / next_row1 give the extent
+ * of the bands above and below (-1 = none).  depth passed to render/stage_downsample is then the
+ * BAND's rows only (row1-row0 rows), and ao_out receives the band's rows only. */
+int meao_set_row_band(MeaoCtx *ctx, int32_t row0, int32_t row1, int32_t prev_row0, int32_t next_row1);
+/* Border rows of LowDepth1..4 that a neighbour needs.  side: 0 = towards row 0 (up), 1 = down.
+ * meao_halo_bytes: size of the packed message this context SENDS to that side (== what the
+ * neighbour's unpack of the opposite side expects). */
+int64_t meao_halo_bytes(MeaoCtx *ctx, int32_t side);
+int64_t meao_halo_recv_bytes(MeaoCtx *ctx, int32_t side);
+/* Row ranges behind those sizes: out8 = {lo1,hi1, lo2,hi2, lo3,hi3, lo4,hi4} rows of LowDepth1..4 that
+ * are sent (send != 0) / received (send == 0) on that side; the packed message is those rows, level 1
+ * first, each row lw[k] tightly packed f32. */
+int meao_halo_rows(MeaoCtx *ctx, int32_t side, int32_t send, int32_t out8[8]);
+/* out30 = for k = 0..4: rows of level k to produce [2k,2k+1]; rows of LowDepth<k> read [10+2k..];
+ * rows of LowDepth<k> this band owns [20+2k..]. */
+int meao_band_rows(MeaoCtx *ctx, int32_t out30[30]);
+int meao_halo_pack(MeaoCtx *ctx, int32_t side, void *packed_dev, void *stream);
+int meao_halo_unpack(MeaoCtx *ctx, int32_t side, const void *packed_dev, void *stream);
+/* Split of meao_render around the exchange: phase A = downsample own rows; (exchange); phase B =
+ * render + upsample. */
+int meao_render_band_prepare(MeaoCtx *ctx, const void *depth_band_dev, int32_t depth_kind, void *stream);
+int meao_render_band_finish(MeaoCtx *ctx, void *ao_band_out_dev, void *stream);
+
+/* ---- command-buffer hook (Unity native-plugin style) -------------------------------------------- */
+/* replaces: camera.AddCommandBuffer(..., _renderCommand) (AO.cs:412-429): a host engine issues
+ * CommandBuffer.IssuePluginEvent(meao_get_render_event_func(), event_id). */
+typedef void (*MeaoRenderEventFunc)(int event_id);
+int meao_bind_event(MeaoCtx *ctx, int32_t event_id, const void *depth_dev, int32_t depth_kind, void *ao_out_dev);
+void meao_render_event(int event_id);
+MeaoRenderEventFunc meao_get_render_event_func(void);
+
+/* ---- introspection ------------------------------------------------------------------------------ */
+int64_t meao_launch_count(const MeaoCtx *ctx);       /* kernels launched (or replayed via graph) so far */
+int meao_kernels_per_frame(const MeaoCtx *ctx);      /* kernel nodes in one frame */
+/* Algorithmic bytes of the reference data-flow: stage 0 = whole frame, 1 = Downsample1,
+ * 2 = Downsample2, 3 = Render x4, 4 = Upsample x4, 5 = final Upsample (L1->L0) only. */
+int64_t meao_algorithmic_bytes(const MeaoCtx *ctx, int32_t stage);
+/* Device time (ms) of the individual kernels of the last meao_profile_frame() call, which runs one
+ * frame with a cudaEvent pair around every kernel.  names/ms arrays of length >= meao_kernels_per_frame(). */
+int meao_profile_frame(MeaoCtx *ctx, const void *depth_dev, int32_t depth_kind, void *ao_out_dev,
+                       float *ms_out, const char **names_out, int32_t capacity);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEAO_H */

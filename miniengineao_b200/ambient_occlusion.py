@@ -1,0 +1,278 @@
+"""Host-side mirror of MiniEngineAO.AmbientOcclusion (Assets/MiniEngineAO/AmbientOcclusion.cs).
+
+Same property names, ranges and defaults (AO.cs:20-68), same re-plan triggers (LateUpdate /
+CheckPropertiesChanged, AO.cs:84-113, 329-350), same constant math -- but the ten compute
+dispatches of the "SSAO" command buffer (AO.cs:511-531) are one call into libmeao.so.
+PyTorch is used only to hold device memory and streams.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native as N
+
+
+@dataclass
+class Camera:
+    """The few UnityEngine.Camera fields the hot path reads (AO.cs:338-341, 561-573)."""
+    pixelWidth: int
+    pixelHeight: int
+    nearClipPlane: float = 0.3
+    farClipPlane: float = 100.0
+    fieldOfView: float = 60.0           # vertical, degrees
+    usesReversedZBuffer: bool = True    # SystemInfo.usesReversedZBuffer on D3D11/12
+
+    @property
+    def aspect(self) -> float:
+        return self.pixelWidth / self.pixelHeight
+
+    @property
+    def projection00(self) -> float:
+        """projectionMatrix[0,0] of a perspective camera."""
+        return 1.0 / (self.aspect * math.tan(math.radians(self.fieldOfView) / 2.0))
+
+
+def _clamp(v, lo, hi):
+    return max(lo, min(hi, v))
+
+
+class AmbientOcclusion:
+    """Drop-in for the compute path of the AmbientOcclusion component."""
+
+    # debug view ids, AO.cs:787-808
+    DEBUG_NAMES = {1: "LinearDepth", 2: "LowDepth1", 3: "LowDepth2", 4: "LowDepth3", 5: "LowDepth4",
+                   6: "TiledDepth1", 7: "TiledDepth2", 8: "TiledDepth3", 9: "TiledDepth4",
+                   10: "Occlusion1", 11: "Occlusion2", 12: "Occlusion3", 13: "Occlusion4",
+                   14: "Combined1", 15: "Combined2", 16: "Combined3", 17: "AmbientOcclusion"}
+
+    def __init__(self, camera: Camera, device: int = 0, use_graph: bool = True):
+        self._lib = N.lib()
+        self._camera = camera
+        cfg = N.MeaoDeviceCfg(device, N.MEAO_FLAG_NONE if use_graph else N.MEAO_FLAG_NO_GRAPH)
+        h = C.c_void_p()
+        rc = self._lib.meao_create(C.byref(cfg), C.byref(h))
+        if rc < 0:
+            msg = self._lib.meao_last_error(None)
+            raise N.MeaoError(rc, msg.decode() if msg else "?")
+        self._ctx = h
+        self.device = device
+        p = N.MeaoParams()
+        self._lib.meao_default_params(C.byref(p))
+        # serialized fields, AO.cs:20-68
+        self._noiseFilterTolerance = p.noise_filter_tolerance
+        self._blurTolerance = p.blur_tolerance
+        self._upsampleTolerance = p.upsample_tolerance
+        self._thicknessModifier = p.thickness_modifier
+        self._intensity = p.intensity
+        self._debug = 0
+        self._ambientOnly = True
+        self.rebuild_count = 0
+        self._width = self._height = 0
+
+    # ---- exposed properties (AO.cs:22-66); Unity clamps to the Range attribute in the inspector only
+    noiseFilterTolerance = property(lambda s: s._noiseFilterTolerance, lambda s, v: setattr(s, "_noiseFilterTolerance", float(v)))
+    blurTolerance = property(lambda s: s._blurTolerance, lambda s, v: setattr(s, "_blurTolerance", float(v)))
+    upsampleTolerance = property(lambda s: s._upsampleTolerance, lambda s, v: setattr(s, "_upsampleTolerance", float(v)))
+    thicknessModifier = property(lambda s: s._thicknessModifier, lambda s, v: setattr(s, "_thicknessModifier", float(v)))
+    intensity = property(lambda s: s._intensity, lambda s, v: setattr(s, "_intensity", float(v)))
+    ambientOnly = property(lambda s: s._ambientOnly, lambda s, v: setattr(s, "_ambientOnly", bool(v)))
+    RANGES = {"noiseFilterTolerance": (-8, 0), "blurTolerance": (-8, -1), "upsampleTolerance": (-12, -1),
+              "thicknessModifier": (1, 10), "intensity": (0, 2), "debug": (0, 17)}
+
+    @property
+    def camera(self) -> Camera:
+        return self._camera
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self._lib.meao_destroy(self._ctx)      # OnDestroy, AO.cs:357-381
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> int:
+        return N.check(self._ctx, rc)
+
+    # ---- LateUpdate: re-plan only when something changed (AO.cs:329-350) ---------------------------
+    def LateUpdate(self) -> bool:
+        cam = self._camera
+        p = N.MeaoParams(self._noiseFilterTolerance, self._blurTolerance, self._upsampleTolerance,
+                         self._thicknessModifier, self._intensity, self._debug, int(self._ambientOnly))
+        rebuild = self._check(self._lib.meao_set_params(self._ctx, C.byref(p))) == 1      # CheckPropertiesChanged
+        c = N.MeaoCamera(cam.nearClipPlane, cam.farClipPlane, 1.0 / cam.projection00, int(cam.usesReversedZBuffer))
+        self._check(self._lib.meao_set_camera(self._ctx, C.byref(c)))
+        resized = self._check(self._lib.meao_resize(self._ctx, cam.pixelWidth, cam.pixelHeight)) == 1  # CheckBaseDimensions
+        self._width, self._height = cam.pixelWidth, cam.pixelHeight
+        if rebuild or resized:
+            self.rebuild_count += 1
+        return rebuild or resized
+
+    # ---- frame ----------------------------------------------------------------------------------
+    def render(self, depth, out=None, *, linear: bool = False, stream=None):
+        """depth: CUDA float32 tensor [H, W] (raw camera depth, or linear if linear=True).
+        Returns a CUDA uint8 tensor [H, W] -- the AmbientOcclusion R8 texture (AO.cs:475)."""
+        import torch
+        self.LateUpdate()
+        if not (depth.is_cuda and depth.dtype == torch.float32 and depth.is_contiguous()):
+            raise ValueError("depth must be a contiguous CUDA float32 tensor")
+        rows = self._band_rows()
+        if tuple(depth.shape) != (rows, self._width):
+            raise ValueError(f"depth shape {tuple(depth.shape)} != {(rows, self._width)}")
+        if out is None:
+            out = torch.empty((rows, self._width), dtype=torch.uint8, device=depth.device)
+        s = stream if stream is not None else torch.cuda.current_stream(depth.device)
+        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        self._check(self._lib.meao_render(self._ctx, depth.data_ptr(), kind, out.data_ptr(), s.cuda_stream))
+        return out
+
+    def render_host(self, depth: np.ndarray, out: np.ndarray | None = None, *, linear: bool = False) -> np.ndarray:
+        """Host float32 [H, W] in, host uint8 [H, W] out (H2D + ten passes + D2H + sync)."""
+        self.LateUpdate()
+        rows = self._band_rows()
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        if d.shape != (rows, self._width):
+            raise ValueError(f"depth shape {d.shape} != {(rows, self._width)}")
+        if out is None:
+            out = np.empty((rows, self._width), np.uint8)
+        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        self._check(self._lib.meao_render_host(self._ctx, d.ctypes.data, kind, out.ctypes.data))
+        return out
+
+    def synchronize(self) -> None:
+        self._check(self._lib.meao_synchronize(self._ctx))
+
+    # ---- stage entry points (mirror Push*Commands) -----------------------------------------------
+    def stage_downsample(self, depth, *, linear: bool = False) -> None:
+        self.LateUpdate()
+        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        self._check(self._lib.meao_stage_downsample(self._ctx, depth.data_ptr(), kind, None))
+
+    def stage_render(self, level: int) -> None:
+        self.LateUpdate()
+        self._check(self._lib.meao_stage_render(self._ctx, level, None))
+
+    def stage_upsample(self, lo_level: int) -> None:
+        self.LateUpdate()
+        self._check(self._lib.meao_stage_upsample(self._ctx, lo_level, None, None))
+
+    # ---- debug views (AO.cs:787-820) ---------------------------------------------------------------
+    def buffer_desc(self, debug_id: int) -> N.MeaoBufferDesc:
+        self.LateUpdate()
+        d = N.MeaoBufferDesc()
+        self._check(self._lib.meao_buffer_desc(self._ctx, debug_id, C.byref(d)))
+        return d
+
+    def debug_buffer(self, debug_id: int) -> np.ndarray:
+        """Buffer <id> in the reference layout and native type: float16 / float32 / uint8 codes."""
+        d = self.buffer_desc(debug_id)
+        dt = {1: np.uint8, 2: np.float16, 4: np.float32}[d.elem_bytes]
+        shape = (d.slices, d.height, d.width) if d.slices > 1 else (d.height, d.width)
+        a = np.empty(shape, dt)
+        self._check(self._lib.meao_get_buffer(self._ctx, debug_id, a.ctypes.data, a.nbytes))
+        return a
+
+    def set_debug_buffer(self, debug_id: int, values: np.ndarray) -> None:
+        d = self.buffer_desc(debug_id)
+        dt = {1: np.uint8, 2: np.float16, 4: np.float32}[d.elem_bytes]
+        a = np.ascontiguousarray(values, dtype=dt)
+        assert a.shape == (d.height, d.width), (a.shape, d.height, d.width)
+        self._check(self._lib.meao_set_buffer(self._ctx, debug_id, a.ctypes.data, a.nbytes))
+
+    # ---- constants ----------------------------------------------------------------------------------
+    def render_constants(self, level: int) -> dict:
+        self.LateUpdate()
+        out = (C.c_float * 28)()
+        self._check(self._lib.meao_render_constants(self._ctx, level, out))
+        a = np.array(out, np.float32)
+        return {"inv_thickness": a[0:12], "sample_weight": a[12:24], "inv_slice_dim": a[24:26],
+                "reject_fadeoff": a[26], "intensity": a[27]}
+
+    def upsample_constants(self, lo_level: int) -> dict:
+        self.LateUpdate()
+        out = (C.c_float * 8)()
+        self._check(self._lib.meao_upsample_constants(self._ctx, lo_level, out))
+        a = np.array(out, np.float32)
+        return {"inv_low": a[0:2], "inv_high": a[2:4], "noise_filter_strength": a[4], "step_size": a[5],
+                "blur_tolerance": a[6], "upsample_tolerance": a[7]}
+
+    def zbuffer_params(self) -> np.ndarray:
+        self.LateUpdate()
+        out = (C.c_float * 4)()
+        self._check(self._lib.meao_zbuffer_params(self._ctx, out))
+        return np.array(out, np.float32)
+
+    # ---- row bands (multi-GPU frame partition) ---------------------------------------------------
+    def set_row_band(self, row0: int, row1: int, prev_row0: int = -1, next_row1: int = -1) -> None:
+        self.LateUpdate()
+        self._check(self._lib.meao_set_row_band(self._ctx, row0, row1, prev_row0, next_row1))
+        self._band = (row0, row1)
+
+    def _band_rows(self) -> int:
+        b = getattr(self, "_band", None)
+        return self._height if b is None else b[1] - b[0]
+
+    def band_rows(self) -> dict:
+        """Row ranges of this band per level: rows to produce, LowDepth rows read, LowDepth rows owned."""
+        self.LateUpdate()
+        out = (C.c_int32 * 30)()
+        self._check(self._lib.meao_band_rows(self._ctx, out))
+        a = list(out)
+        return {"produce": [(a[2 * k], a[2 * k + 1]) for k in range(5)],
+                "need_low": [(a[10 + 2 * k], a[11 + 2 * k]) for k in range(5)],
+                "own_low": [(a[20 + 2 * k], a[21 + 2 * k]) for k in range(5)]}
+
+    def halo_rows(self, side: int, send: bool) -> list[tuple[int, int]]:
+        """[(lo, hi)] rows of LowDepth1..4 sent to / received from `side` (0 = up, 1 = down)."""
+        out = (C.c_int32 * 8)()
+        self._check(self._lib.meao_halo_rows(self._ctx, side, int(send), out))
+        return [(out[2 * i], out[2 * i + 1]) for i in range(4)]
+
+    def halo_bytes(self, side: int) -> int:
+        return self._check(self._lib.meao_halo_bytes(self._ctx, side))
+
+    def halo_recv_bytes(self, side: int) -> int:
+        return self._check(self._lib.meao_halo_recv_bytes(self._ctx, side))
+
+    def halo_pack(self, side: int, buf, stream=None) -> None:
+        self._check(self._lib.meao_halo_pack(self._ctx, side, buf.data_ptr(), stream.cuda_stream if stream else None))
+
+    def halo_unpack(self, side: int, buf, stream=None) -> None:
+        self._check(self._lib.meao_halo_unpack(self._ctx, side, buf.data_ptr(), stream.cuda_stream if stream else None))
+
+    def band_prepare(self, depth_band, *, linear: bool = False, stream=None) -> None:
+        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        self._check(self._lib.meao_render_band_prepare(self._ctx, depth_band.data_ptr(), kind,
+                                                       stream.cuda_stream if stream else None))
+
+    def band_finish(self, out_band, stream=None) -> None:
+        self._check(self._lib.meao_render_band_finish(self._ctx, out_band.data_ptr(), stream.cuda_stream if stream else None))
+
+    # ---- introspection ----------------------------------------------------------------------------
+    @property
+    def launch_count(self) -> int:
+        return self._lib.meao_launch_count(self._ctx)
+
+    @property
+    def kernels_per_frame(self) -> int:
+        return self._lib.meao_kernels_per_frame(self._ctx)
+
+    def algorithmic_bytes(self, stage: int = 0) -> int:
+        self.LateUpdate()
+        return self._check(self._lib.meao_algorithmic_bytes(self._ctx, stage))
+
+    def profile_frame(self, depth, out, *, linear: bool = False) -> list[tuple[str, float]]:
+        self.LateUpdate()
+        n = self.kernels_per_frame
+        ms = (C.c_float * n)()
+        names = (C.c_char_p * n)()
+        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        k = self._check(self._lib.meao_profile_frame(self._ctx, depth.data_ptr(), kind, out.data_ptr(), ms, names, n))
+        return [(names[i].decode(), float(ms[i])) for i in range(k)]

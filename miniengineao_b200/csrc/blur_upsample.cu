@@ -1,0 +1,281 @@
+// blur_upsample.cu -- stage 3 of the SSAO pipe: depth-aware 5x5 separable blur of the low-res AO
+// followed by a 4-tap bilateral upsample (optionally multiplied by the hi-res AO).
+//
+// Replaces Upsample.compute kernels main / main_blendout (PrefetchData :54-72, SmartBlur :74-81,
+// CompareDeltas :83-87, BlurHorizontally :89-130, BlurVertically :132-170, BilateralUpsample
+// :177-183, MAIN :185-233).
+//
+// Design (not a port): the reference maps one thread to a 2x2 output quad with an 8x8 group and a
+// 16x16 LDS tile (3.5x apron overhead, 39/64 and 45/64 lanes active in the blur).  Here a CTA owns
+// a 64x32 tile of HI-res outputs; the 38x22 low-res footprint (depth f32 + AO unorm8) arrives by two
+// TMA box loads, the blur runs on 4-wide / 3-tall register runs so neighbouring outputs share
+// their depth deltas, and the upsample streams hi-res depth / AO / result with 128-/64-bit
+// accesses, 8 pixels per thread.
+//
+// The blurred value B(vx,vy) is a pure function of the low-res texels clamp(vx+dx), clamp(vy+dy)
+// for |dx|,|dy| <= 2 (point + clamp Gather, UPS:56,67) and is defined for the virtual coordinates
+// vx in [-1, low.w], so it does not depend on the reference's group tiling.  Hi-res pixel (px,py)
+// uses the quad X-1..X, Y-1..Y with X = (px+1)>>1, Y = (py+1)>>1 and the weight order of
+// UPS:229-232.
+//
+// Bound: mixed -- 5 IEEE divisions per output pixel make the final level issue-heavy next to
+// its 2+1+1 B/px of HBM traffic.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace meao {
+
+namespace {
+
+constexpr int kHW = 64, kHH = 32;               // hi-res outputs per CTA
+constexpr int kRawW = 38, kRawH = 22;           // low-res footprint actually used
+constexpr int kRawP = kUpsDepthBoxW;            // 40: pitch of the raw arrays (== depth box width)
+constexpr int kAoP = kUpsAoBoxW;                // 48: pitch of the raw unorm8 tile (== AO box width)
+constexpr int kBlurW = 34, kBlurH = 18;         // blurred texels needed
+constexpr int kBlurP = 36;                      // pitch of the blurred arrays
+constexpr int kThreads = 256;
+static_assert(kRawH == kUpsDepthBoxH && kRawH == kUpsAoBoxH, "TMA box mismatch");
+
+struct __align__(128) Smem {
+    alignas(128) float lo_depth[kRawH * kRawP];     // raw low-res depth (LoResDB), TMA destination
+    alignas(128) uint8_t ao_raw[kRawH * kAoP];      // raw low-res AO codes (LoResAO1), TMA destination
+    alignas(16) float inv_depth[kRawH * kRawP];     // DepthCache, UPS:67-71
+    alignas(16) float ao[kRawH * kRawP];            // AOCache1 as loaded, UPS:62-65
+    alignas(16) float hblur[kRawH * kBlurP];        // AOCache2, UPS:127-129
+    alignas(16) float vblur[kBlurH * kBlurP];       // AOCache1 after the vertical pass, UPS:168-169
+    alignas(8) uint64_t bar;
+};
+
+// Upsample.compute:74-81.  /2 and /4 are exact scalings.
+__device__ __forceinline__ float smart_blur(float a, float b, float c, float d, float e, bool Left, bool Middle, bool Right)
+{
+    b = (Left | Middle) ? b : c;
+    a = Left ? a : b;
+    d = (Right | Middle) ? d : c;
+    e = Right ? e : d;
+    const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(a, e), 0.5f), b), c), d);
+    return __fmul_rn(s, 0.25f);
+}
+
+// Upsample.compute:83-87
+__device__ __forceinline__ bool compare_deltas(float d1, float d2, float l1, float l2, float step, float kblur)
+{
+    const float temp = fmaf(d1, d2, step);
+    return __fmul_rn(temp, temp) > __fmul_rn(__fmul_rn(l1, l2), kblur);
+}
+
+// Upsample.compute:177-183 with the swizzled argument order of :229-232
+__device__ __forceinline__ float bilateral(float hi_depth, float hi_ao,
+                                           float ld0, float ld1, float ld2, float ld3,
+                                           float la0, float la1, float la2, float la3,
+                                           float tol, float nfs)
+{
+    const float w0 = 9.0f / __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld0)), tol);
+    const float w1 = 3.0f / __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld1)), tol);
+    const float w2 = 1.0f / __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld2)), tol);
+    const float w3 = 3.0f / __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld3)), tol);
+    const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(w0, w1), w2), w3), nfs);
+    const float wsum = __fadd_rn(fmaf(la3, w3, fmaf(la2, w2, fmaf(la1, w1, __fmul_rn(la0, w0)))), nfs);
+    return __fmul_rn(hi_ao, wsum) / total;
+}
+
+template <bool BLEND, bool HI_HALF>
+__global__ void __launch_bounds__(kThreads)
+blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __grid_constant__ CUtensorMap lo_ao_map,
+                     const UpsampleArgs a, const int use_tma)
+{
+#ifdef MEAO_DEVICE_OK
+    __shared__ Smem sm;
+    const int tid = threadIdx.x;
+    const int hx0 = blockIdx.x * kHW;
+    const int hy0 = (a.row0 & ~1) + blockIdx.y * kHH;
+    const int lx0 = (hx0 >> 1) - 3, ly0 = (hy0 >> 1) - 3;      // virtual low-res coordinate of raw tile (0,0)
+
+    const bool interior = use_tma && lx0 >= 0 && ly0 >= 0 && (lx0 + kRawW <= a.low) && (ly0 + kRawH <= a.loh);
+    if (interior) {
+        if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&sm.bar, (uint32_t)(kRawH * kRawP * sizeof(float) + kRawH * kAoP));
+            tma_load_2d(sm.lo_depth, &lo_depth_map, lx0, ly0, &sm.bar);
+            tma_load_2d(sm.ao_raw, &lo_ao_map, lx0, ly0, &sm.bar);
+        }
+        mbar_wait(&sm.bar, 0);
+        for (int idx = tid; idx < kRawH * kRawP; idx += kThreads) {
+            const int r = idx / kRawP, c = idx - r * kRawP;
+            sm.inv_depth[r * kRawP + c] = 1.0f / sm.lo_depth[r * kRawP + c];            // UPS:67
+            sm.ao[r * kRawP + c] = unorm8_load(sm.ao_raw[r * kAoP + c]);
+        }
+    } else {
+        // border tile: point + clamp addressing (UPS:56,67)
+        for (int idx = tid; idx < kRawH * kRawP; idx += kThreads) {
+            const int r = idx / kRawP, c = idx - r * kRawP;
+            const int sx = iclamp(lx0 + c, 0, a.low - 1), sy = iclamp(ly0 + r, 0, a.loh - 1);
+            const float d = __ldg(a.lo_depth + (size_t)sy * a.lo_dpitch + sx);
+            sm.lo_depth[r * kRawP + c] = d;
+            sm.inv_depth[r * kRawP + c] = 1.0f / d;
+            sm.ao[r * kRawP + c] = unorm8_load(__ldg(a.lo_ao + (size_t)sy * a.lo_apitch + sx));
+        }
+    }
+    __syncthreads();
+
+    const float step = a.step_size, kblur = a.blur_tolerance;
+
+    // ---- horizontal blur, UPS:89-130: 22 rows x 9 runs of 4 outputs; output c is centred on raw c+2
+    if (tid < kRawH * 9) {
+        const int r = tid / 9, c0 = (tid - r * 9) * 4;
+        const float4 A0 = *reinterpret_cast<const float4 *>(&sm.ao[r * kRawP + c0]);
+        const float4 A1 = *reinterpret_cast<const float4 *>(&sm.ao[r * kRawP + c0 + 4]);
+        const float4 D0 = *reinterpret_cast<const float4 *>(&sm.inv_depth[r * kRawP + c0]);
+        const float4 D1 = *reinterpret_cast<const float4 *>(&sm.inv_depth[r * kRawP + c0 + 4]);
+        const float av[8] = {A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, A1.z, A1.w};
+        const float dv[8] = {D0.x, D0.y, D0.z, D0.w, D1.x, D1.y, D1.z, D1.w};
+        float dd[7], ll[7];
+        bool cc[6];
+#pragma unroll
+        for (int i = 0; i < 7; i++) { dd[i] = __fadd_rn(dv[i + 1], -dv[i]); ll[i] = fmaf(dd[i], dd[i], step); }
+#pragma unroll
+        for (int i = 0; i < 6; i++) cc[i] = compare_deltas(dd[i], dd[i + 1], ll[i], ll[i + 1], step, kblur);
+        float4 o;
+        o.x = smart_blur(av[0], av[1], av[2], av[3], av[4], cc[0], cc[1], cc[2]);
+        o.y = smart_blur(av[1], av[2], av[3], av[4], av[5], cc[1], cc[2], cc[3]);
+        o.z = smart_blur(av[2], av[3], av[4], av[5], av[6], cc[2], cc[3], cc[4]);
+        o.w = smart_blur(av[3], av[4], av[5], av[6], av[7], cc[3], cc[4], cc[5]);
+        *reinterpret_cast<float4 *>(&sm.hblur[r * kBlurP + c0]) = o;
+    }
+    __syncthreads();
+
+    // ---- vertical blur, UPS:132-170: 34 columns x 6 runs of 3 outputs; output r centred on row r+2,
+    //      depth column offset +2 (UPS:141-146)
+    if (tid < kBlurW * 6) {
+        const int run = tid / kBlurW, c = tid - run * kBlurW, r0 = run * 3;
+        float av[7], dv[7], dd[6], ll[6];
+        bool cc[5];
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            av[i] = sm.hblur[(r0 + i) * kBlurP + c];
+            dv[i] = sm.inv_depth[(r0 + i) * kRawP + c + 2];
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++) { dd[i] = __fadd_rn(dv[i + 1], -dv[i]); ll[i] = fmaf(dd[i], dd[i], step); }
+#pragma unroll
+        for (int i = 0; i < 5; i++) cc[i] = compare_deltas(dd[i], dd[i + 1], ll[i], ll[i + 1], step, kblur);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            sm.vblur[(r0 + i) * kBlurP + c] = smart_blur(av[i], av[i + 1], av[i + 2], av[i + 3], av[i + 4], cc[i], cc[i + 1], cc[i + 2]);
+    }
+    __syncthreads();
+
+    // ---- bilateral upsample, UPS:213-232: thread -> 8 consecutive hi-res pixels of one row ----------
+    const int j = tid & 7, hy = tid >> 3;
+    const int py = hy0 + hy, px0 = hx0 + 8 * j;
+    if (py < a.row0 || py >= a.row1 || px0 >= a.hiw) return;
+
+    // blurred index of X-1 for the first pixel is 4j; quad rows: rY-1, rY with rY = ((hy+1)>>1)+1
+    const int rY = ((hy + 1) >> 1) + 1;
+    float bl_ao[2][6], lo_d[2][6];      // [0] = row Y-1 (top), [1] = row Y (bottom)
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const float *vb = &sm.vblur[(rY - 1 + rr) * kBlurP + 4 * j];
+        const float *ld = &sm.lo_depth[(rY - 1 + rr + 2) * kRawP + 4 * j + 2];
+        const float4 v4 = *reinterpret_cast<const float4 *>(vb);
+        const float2 v2 = *reinterpret_cast<const float2 *>(vb + 4);
+        bl_ao[rr][0] = v4.x; bl_ao[rr][1] = v4.y; bl_ao[rr][2] = v4.z; bl_ao[rr][3] = v4.w; bl_ao[rr][4] = v2.x; bl_ao[rr][5] = v2.y;
+        const float2 d0 = *reinterpret_cast<const float2 *>(ld);
+        const float2 d1 = *reinterpret_cast<const float2 *>(ld + 2);
+        const float2 d2 = *reinterpret_cast<const float2 *>(ld + 4);
+        lo_d[rr][0] = d0.x; lo_d[rr][1] = d0.y; lo_d[rr][2] = d1.x; lo_d[rr][3] = d1.y; lo_d[rr][4] = d2.x; lo_d[rr][5] = d2.y;
+    }
+
+    const bool full = (px0 + 8 <= a.hiw);
+    float hd[8], ha[8];
+    if (HI_HALF) {
+        const __half *src = reinterpret_cast<const __half *>(a.hi_depth) + (size_t)py * a.hi_dpitch + px0;
+        if (full) {
+            const uint4 q = ldg_stream_u4(src);
+            const __half2 *h = reinterpret_cast<const __half2 *>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const float2 f = __half22float2(h[e]); hd[2 * e] = f.x; hd[2 * e + 1] = f.y; }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) hd[e] = (px0 + e < a.hiw) ? __half2float(src[e]) : 1.0f;
+        }
+    } else {
+        const float *src = reinterpret_cast<const float *>(a.hi_depth) + (size_t)py * a.hi_dpitch + px0;
+        if (full) {
+            const float4 q0 = ldg_stream_f4(src), q1 = ldg_stream_f4(src + 4);
+            hd[0] = q0.x; hd[1] = q0.y; hd[2] = q0.z; hd[3] = q0.w; hd[4] = q1.x; hd[5] = q1.y; hd[6] = q1.z; hd[7] = q1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) hd[e] = (px0 + e < a.hiw) ? __ldg(src + e) : 1.0f;
+        }
+    }
+    if (BLEND) {
+        const uint8_t *src = a.hi_ao + (size_t)py * a.hi_apitch + px0;
+        if (full) {
+            const uint2 q = ldg_stream_u2(src);
+#pragma unroll
+            for (int e = 0; e < 4; e++) { ha[e] = unorm8_load((q.x >> (8 * e)) & 0xffu); ha[4 + e] = unorm8_load((q.y >> (8 * e)) & 0xffu); }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) ha[e] = (px0 + e < a.hiw) ? unorm8_load(__ldg(src + e)) : 1.0f;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) ha[e] = 1.0f;                                            // UPS:223
+    }
+
+    const float tol = a.upsample_tolerance, nfs = a.noise_filter_strength;
+    const bool y_odd = (py & 1) != 0;     // py = 2Y-1 (odd) or 2Y (even)
+    uint32_t code[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        // X - 1 -> local index m, X -> m + 1, with m = (e + 1) >> 1 relative to blurred column 4j
+        const int m = (e + 1) >> 1;
+        const float tl_d = lo_d[0][m], tr_d = lo_d[0][m + 1], bl_d = lo_d[1][m], br_d = lo_d[1][m + 1];
+        const float tl_a = bl_ao[0][m], tr_a = bl_ao[0][m + 1], bl_a = bl_ao[1][m], br_a = bl_ao[1][m + 1];
+        float r;
+        if ((e & 1) != 0) {            // px odd = 2X-1
+            if (!y_odd) r = bilateral(hd[e], ha[e], bl_d, br_d, tr_d, tl_d, bl_a, br_a, tr_a, tl_a, tol, nfs);   // UPS:229 (-1, 0) .xyzw
+            else        r = bilateral(hd[e], ha[e], tl_d, bl_d, br_d, tr_d, tl_a, bl_a, br_a, tr_a, tol, nfs);   // UPS:232 (-1,-1) .wxyz
+        } else {                       // px even = 2X
+            if (!y_odd) r = bilateral(hd[e], ha[e], br_d, tr_d, tl_d, bl_d, br_a, tr_a, tl_a, bl_a, tol, nfs);   // UPS:230 ( 0, 0) .yzwx
+            else        r = bilateral(hd[e], ha[e], tr_d, tl_d, bl_d, br_d, tr_a, tl_a, bl_a, br_a, tol, nfs);   // UPS:231 ( 0,-1) .zwxy
+        }
+        code[e] = unorm8_code(r);
+    }
+
+    uint8_t *dst = a.out + (size_t)(py - a.out_row_origin) * a.out_pitch + px0;
+    if (full && a.out_vec_ok) {
+        uint2 pk;
+        pk.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+        pk.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+        *reinterpret_cast<uint2 *>(dst) = pk;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+            if (px0 + e < a.hiw) dst[e] = (uint8_t)code[e];
+    }
+#endif
+}
+
+}  // namespace
+
+cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensorMap &lo_ao_map, bool use_tma,
+                                 const UpsampleArgs &a, cudaStream_t s)
+{
+    if (a.row1 <= a.row0) return cudaSuccess;
+    const int ybase = a.row0 & ~1;
+    dim3 grid(ceil_div(a.hiw, kHW), ceil_div(a.row1 - ybase, kHH));
+    const int t = use_tma ? 1 : 0;
+    if (a.hi_ao) {
+        if (a.hi_is_half) blur_upsample_kernel<true, true><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, a, t);
+        else              blur_upsample_kernel<true, false><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, a, t);
+    } else {
+        if (a.hi_is_half) blur_upsample_kernel<false, true><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, a, t);
+        else              blur_upsample_kernel<false, false><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, a, t);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace meao

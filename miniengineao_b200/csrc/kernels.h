@@ -1,0 +1,83 @@
+// kernels.h -- argument blocks and host-side launchers of the three libmeao pipeline stages.
+//
+// All intermediate buffers live in HBM in NATURAL (row-major, non-deinterleaved) layout with
+// global frame coordinates; rows are pitched to 128 bytes.  The four 16-slice TiledDepth atlases
+// of the reference (Downsample1.compute:71,78, Downsample2.compute:41,49) are never materialised:
+// the render kernel reads LowDepth<k> and applies the f16 rounding, the slice-space clamp and the
+// atlas padding values itself (see render_ao.cu).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace meao {
+
+// ---- stage 1: prepare_depth = Downsample1.compute + Downsample2.compute fused ----------------
+struct PrepareArgs {
+    const float *depth;     // input rows [depth_row0, ...) of the frame, row pitch = W floats
+    int W, H;               // full-frame size
+    int depth_row0;         // global row of depth[0]
+    int row0, row1;         // global L0 rows to process; row0 % 16 == 0
+    __half *lin;            // LinearDepth, L0, f16
+    int lin_pitch;          // elements
+    float *low[4];          // LowDepth1..4, f32
+    int low_pitch[4];       // elements
+    float zbx, zby;         // ZBufferParams.xy (AmbientOcclusion.cs:561-568)
+    int raw;                // 1: Linearize (DS1:37-48); 0: depth is already linear
+    int reversed_z;         // UNITY_REVERSED_Z (DS1:41-45)
+    int vec_ok;             // depth pointer 16B aligned and W % 4 == 0
+};
+cudaError_t launch_prepare_depth(const PrepareArgs &a, cudaStream_t s);
+
+// ---- stage 2: render_ao = Render.compute main_interleaved, one mip level -----------------------
+struct RenderArgs {
+    const float *low;       // LowDepth<k>
+    int lw, lh, lpitch;     // size of level k, pitch in elements
+    uint8_t *occ;           // Occlusion<k>, unorm8
+    int opitch;
+    int sw, sh;             // size of the (virtual) TiledDepth<k> slice = level k+2
+    float pad;              // value of atlas padding texels (already f16-rounded): Linearize(0) for k=1,2; 0 for k=3,4
+    float inv_thickness[7]; // gInvThicknessTable entries used by Render.compute:162-168, in call order
+    float neg_front[7];     // -(invThickness - 0.5)  (Render.compute:85)
+    float weight[7];        // gSampleWeightTable entries, same order
+    float reject_fadeoff;   // gRejectFadeoff
+    float intensity;        // gIntensity
+    int row0, row1;         // output rows (level k) to produce
+};
+cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const RenderArgs &a, cudaStream_t s);
+constexpr int kRenderBoxW = 96, kRenderBoxH = 64;     // TMA box of the render kernel (f32 elements)
+
+// ---- stage 3: blur_upsample = Upsample.compute main / main_blendout, one level ----------------
+struct UpsampleArgs {
+    const float *lo_depth;  // LoResDB  (LowDepth<lo>)
+    int low, loh, lo_dpitch;
+    const uint8_t *lo_ao;   // LoResAO1 (Occlusion4 or Combined<lo>)
+    int lo_apitch;
+    const void *hi_depth;   // HiResDB  (LowDepth<hi> f32, or LinearDepth f16 when hi == 0)
+    int hi_is_half;
+    int hi_dpitch;
+    const uint8_t *hi_ao;   // HiResAO (Occlusion<hi>) or nullptr => kernel "main" (Upsample.compute:223)
+    int hi_apitch;
+    uint8_t *out;           // AoResult
+    int out_pitch;
+    int out_row_origin;     // global row stored at out[0]
+    int out_vec_ok;         // out is 8B aligned and out_pitch % 8 == 0
+    int hiw, hih;
+    float noise_filter_strength, step_size, blur_tolerance, upsample_tolerance;
+    int row0, row1;         // output rows (hi level) to produce
+};
+cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensorMap &lo_ao_map, bool use_tma,
+                                 const UpsampleArgs &a, cudaStream_t s);
+constexpr int kUpsDepthBoxW = 40, kUpsDepthBoxH = 22; // TMA boxes of the upsample kernel
+constexpr int kUpsAoBoxW = 48, kUpsAoBoxH = 22;
+
+// ---- debug: synthesise a TiledDepth<k> view (reference layout [16][sh][sw], f16 bits) ----------
+cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int sw, int sh, float pad,
+                               __half *out, cudaStream_t s);
+
+// ---- halo pack / unpack: rows [r0, r1) of a pitched buffer <-> contiguous staging --------------
+// (plain cudaMemcpy2DAsync is used; no kernel)
+
+}  // namespace meao

@@ -1,0 +1,922 @@
+// meao_api.cu -- context, planner and C ABI of libmeao.so (see include/meao.h).
+//
+// Host-side mirror of the parts of AmbientOcclusion.cs that own the hot path:
+//   RTHandle geometry/formats (AO.cs:124-282), the CPU constant math of the three Push*Commands
+//   recorders (AO.cs:561-593, 660-734, 750-771), the record order of RebuildCommandBuffers
+//   (AO.cs:511-531) and the re-plan triggers of LateUpdate (AO.cs:329-350).
+// "Plan once, replay per frame" maps to: constants + TMA descriptors are rebuilt only when a
+// parameter, the camera or the size changes; a frame is then ten kernel launches (or one CUDA
+// graph launch) on one stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/meao.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace meao;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Range { int lo, hi; };   // [lo, hi)
+inline Range clampr(Range r, int n) { Range o{r.lo < 0 ? 0 : r.lo, r.hi > n ? n : r.hi}; if (o.hi < o.lo) o.hi = o.lo; return o; }
+inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// cuTensorMapEncodeTiled is fetched through the runtime so libmeao.so has no link-time
+// dependency on libcuda (it must load on a machine without a driver for the ABI tests).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Plan {
+    // Render (per level 1..4) -- AO.cs:660-734
+    float inv_thickness[5][12];
+    float sample_weight[5][12];
+    float inv_slice_dim[5][2];
+    float reject_fadeoff;
+    float intensity;
+    float pad[5];
+    // Upsample (per lo level 1..4) -- AO.cs:750-771
+    float inv_low[5][2], inv_high[5][2];
+    float noise_filter_strength[5], step_size[5], blur_tolerance[5], upsample_tolerance[5];
+    float zb[4];
+};
+
+}  // namespace
+
+struct MeaoCtx {
+    int device = 0;
+    bool plan_only = false;                 // device < 0: host-side planning only (no CUDA calls at all)
+    uint32_t flags = 0;
+    std::string error;
+    cudaStream_t stream = nullptr;
+    PFN_encodeTiled encode = nullptr;
+
+    MeaoParams params;
+    MeaoCamera camera;
+    bool plan_dirty = true;
+    Plan plan;
+
+    int W = 0, H = 0;
+    int lw[7] = {0}, lh[7] = {0};
+    // band (global L0 rows) + neighbours
+    int band0 = 0, band1 = 0, prev0 = -1, next1 = -1;
+
+    // device buffers (natural layout, pitched, global coordinates)
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    __half *lin = nullptr; int lin_pitch = 0;
+    float *low[5] = {nullptr}; int low_pitch[5] = {0};
+    uint8_t *occ[5] = {nullptr}; int occ_pitch[5] = {0};
+    uint8_t *comb[4] = {nullptr};           // same pitch as occ of that level
+    uint8_t *result = nullptr; int result_pitch = 0;
+    // staging for the host path
+    float *depth_stage = nullptr;           // device, W*H
+    uint8_t *ao_stage = nullptr;            // device, W*H
+
+    bool tma_ok = false;
+    CUtensorMap map_low_ren[5];             // LowDepth<k> with the render box
+    CUtensorMap map_low_ups[5];             // LowDepth<k> with the upsample depth box
+    CUtensorMap map_ao_ups[5];              // lo AO of upsample lo level k (Occlusion4 / Combined k)
+
+    // row ranges (per level) for this band
+    Range need_c[5];                        // rows of Occlusion<k>/Combined<k> to produce (k=1..4); [0] = final rows
+    Range need_low[5];                      // rows of LowDepth<k> required
+    Range own_low[5];                       // rows of LowDepth<k> this band produces
+
+    int64_t launches = 0;
+
+    // CUDA graph cache (one entry: last (depth, out, kind, stream-independent))
+    cudaGraphExec_t graph_exec = nullptr;
+    const void *graph_depth = nullptr; void *graph_out = nullptr; int graph_kind = -1;
+    int last_kind = MEAO_DEPTH_RAW_F32;     // ingest kind of the last downsample (selects the atlas padding value)
+
+    std::vector<std::pair<std::string, float>> last_profile;
+};
+
+namespace {
+
+int fail(MeaoCtx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->error = buf; else g_create_error = buf;
+    return code;
+}
+#define CUDA_TRY(c, expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) \
+    return fail((c), MEAO_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
+
+// Mathf.Sqrt / Mathf.Pow are (float)Math.X((double)...) in Unity
+float mathf_sqrt(float f) { return (float)std::sqrt((double)f); }
+float mathf_pow(float f, float p) { return (float)std::pow((double)f, (double)p); }
+
+float host_f16_round(float x) { return __half2float(__float2half_rn(x)); }
+
+// AO.cs:577-590
+void sample_thickness(float t[12])
+{
+    t[0] = mathf_sqrt(1 - 0.2f * 0.2f);                 t[1] = mathf_sqrt(1 - 0.4f * 0.4f);
+    t[2] = mathf_sqrt(1 - 0.6f * 0.6f);                 t[3] = mathf_sqrt(1 - 0.8f * 0.8f);
+    t[4] = mathf_sqrt(1 - 0.2f * 0.2f - 0.2f * 0.2f);   t[5] = mathf_sqrt(1 - 0.2f * 0.2f - 0.4f * 0.4f);
+    t[6] = mathf_sqrt(1 - 0.2f * 0.2f - 0.6f * 0.6f);   t[7] = mathf_sqrt(1 - 0.2f * 0.2f - 0.8f * 0.8f);
+    t[8] = mathf_sqrt(1 - 0.4f * 0.4f - 0.4f * 0.4f);   t[9] = mathf_sqrt(1 - 0.4f * 0.4f - 0.6f * 0.6f);
+    t[10] = mathf_sqrt(1 - 0.4f * 0.4f - 0.8f * 0.8f);  t[11] = mathf_sqrt(1 - 0.6f * 0.6f - 0.6f * 0.6f);
+}
+
+// Rebuild the per-dispatch constants (the CPU half of RebuildCommandBuffers, AO.cs:496-540).
+void build_plan(MeaoCtx *c)
+{
+    Plan &p = c->plan;
+    // AO.cs:561-568
+    const float fpn = c->camera.far_clip / c->camera.near_clip;
+    if (c->camera.reversed_z) { p.zb[0] = fpn - 1; p.zb[1] = 1; } else { p.zb[0] = 1 - fpn; p.zb[1] = fpn; }
+    p.zb[2] = p.zb[3] = 0;
+
+    float thick[12];
+    sample_thickness(thick);
+    for (int k = 1; k <= 4; k++) {
+        const int src_w = c->lw[k + 2], src_h = c->lh[k + 2];
+        const float ScreenspaceDiameter = 10;                                                        // AO.cs:669
+        float ThicknessMultiplier = 2 * c->camera.tan_half_fov_h * ScreenspaceDiameter / src_w;     // AO.cs:678
+        float InverseRangeFactor = 1 / ThicknessMultiplier;                                          // AO.cs:683
+        for (int i = 0; i < 12; i++) p.inv_thickness[k][i] = InverseRangeFactor / thick[i];          // AO.cs:687-688
+        static const float mult[12] = {4, 4, 4, 4, 4, 8, 8, 8, 4, 8, 8, 4};                          // AO.cs:696-707
+        float *w = p.sample_weight[k];
+        for (int i = 0; i < 12; i++) w[i] = mult[i] * thick[i];
+        w[0] = 0; w[2] = 0; w[5] = 0; w[7] = 0; w[9] = 0;                                            // AO.cs:711-715
+        float total = 0.0f;
+        for (int i = 0; i < 12; i++) total += w[i];                                                  // AO.cs:718-721
+        for (int i = 0; i < 12; i++) w[i] /= total;                                                  // AO.cs:723-724
+        p.inv_slice_dim[k][0] = 1.0f / src_w; p.inv_slice_dim[k][1] = 1.0f / src_h;                  // AO.cs:732
+        // value of the atlas padding texels: Downsample1 writes Linearize(OOB load = 0),
+        // Downsample2 writes 0 (its OOB load of DS4x)
+        float pad = 0.0f;
+        if (k <= 2) {
+            // raw depth 0 through Linearize (DS1:40-45); linear ingest: 0
+            pad = c->camera.reversed_z ? 1e5f : 1.0f / std::fmaf(p.zb[0], 0.0f, p.zb[1]);
+        }
+        p.pad[k] = pad;   // the depth-kind dependent part (linear ingest -> 0) is applied at launch
+    }
+    p.reject_fadeoff = -1 / c->params.thickness_modifier;                                            // AO.cs:733
+    p.intensity = c->params.intensity;                                                               // AO.cs:734
+
+    for (int lo = 1; lo <= 4; lo++) {
+        const int lo_w = c->lw[lo], lo_h = c->lh[lo], hi_w = c->lw[lo - 1], hi_h = c->lh[lo - 1];
+        float stepSize = 1920.0f / lo_w;                                                             // AO.cs:760
+        float blurTolerance = 1 - mathf_pow(10, c->params.blur_tolerance) * stepSize;                // AO.cs:761
+        blurTolerance *= blurTolerance;                                                              // AO.cs:762
+        float upsampleTolerance = mathf_pow(10, c->params.upsample_tolerance);                       // AO.cs:763
+        float noiseFilterWeight = 1 / (mathf_pow(10, c->params.noise_filter_tolerance) + upsampleTolerance);   // AO.cs:764
+        p.inv_low[lo][0] = 1.0f / lo_w; p.inv_low[lo][1] = 1.0f / lo_h;                              // AO.cs:766
+        p.inv_high[lo][0] = 1.0f / hi_w; p.inv_high[lo][1] = 1.0f / hi_h;                            // AO.cs:767
+        p.noise_filter_strength[lo] = noiseFilterWeight;
+        p.step_size[lo] = stepSize;
+        p.blur_tolerance[lo] = blurTolerance;
+        p.upsample_tolerance[lo] = upsampleTolerance;
+    }
+    c->plan_dirty = false;
+}
+
+void drop_graph(MeaoCtx *c)
+{
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    c->graph_depth = nullptr; c->graph_out = nullptr; c->graph_kind = -1;
+}
+
+void free_buffers(MeaoCtx *c)
+{
+    drop_graph(c);
+    if (c->arena) cudaFree(c->arena);
+    c->arena = nullptr; c->arena_bytes = 0;
+    c->depth_stage = nullptr; c->ao_stage = nullptr;
+}
+
+int make_map(MeaoCtx *c, CUtensorMap *m, CUtensorMapDataType dt, int elem, void *base, int w, int h, int pitch_elems, int bw, int bh)
+{
+    cuuint64_t dims[2] = {(cuuint64_t)w, (cuuint64_t)h};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * elem};
+    cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = c->encode(m, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+// rows of the low level (after clamping) that an upsample producing hi rows [a,b) reads
+Range ups_lo_rows(Range hi, int loh)
+{
+    if (hi.hi <= hi.lo) return Range{0, 0};
+    const int ymin = (hi.lo + 1) >> 1, ymax = hi.hi >> 1;      // Y = (py+1)>>1 for py in [a, b-1]
+    return clampr(Range{ymin - 3, ymax + 3}, loh);             // quad rows Y-1..Y, blur radius 2
+}
+// rows of LowDepth<k> that a render producing rows [a,b) of level k reads (slice texel +-4 => +-16 rows, slice aligned)
+Range ren_low_rows(Range out, int lh)
+{
+    if (out.hi <= out.lo) return Range{0, 0};
+    return clampr(Range{4 * ((out.lo >> 2) - 4), 4 * (((out.hi - 1) >> 2) + 4) + 4}, lh);
+}
+
+struct BandNeeds { Range need_c[5]; Range need_low[5]; Range own_low[5]; };
+
+BandNeeds compute_needs(const MeaoCtx *c, int b0, int b1)
+{
+    BandNeeds n;
+    n.need_c[0] = Range{b0, b1};
+    for (int k = 1; k <= 4; k++) n.need_c[k] = ups_lo_rows(n.need_c[k - 1], c->lh[k]);
+    for (int k = 1; k <= 4; k++) {
+        Range r = ren_low_rows(n.need_c[k], c->lh[k]);
+        // the upsample also reads LowDepth<k> on need_c[k] (as lo depth) -- a subset of r
+        if (n.need_c[k].lo < r.lo) r.lo = n.need_c[k].lo;
+        if (n.need_c[k].hi > r.hi) r.hi = n.need_c[k].hi;
+        n.need_low[k] = r;
+        n.own_low[k] = Range{b0 >> k, (b1 + (1 << k) - 1) >> k};
+    }
+    n.need_low[0] = n.own_low[0] = Range{b0, b1};
+    return n;
+}
+
+int setup_band(MeaoCtx *c)
+{
+    BandNeeds n = compute_needs(c, c->band0, c->band1);
+    for (int k = 0; k <= 4; k++) { c->need_c[k] = n.need_c[k]; c->need_low[k] = n.need_low[k]; c->own_low[k] = n.own_low[k]; }
+    for (int k = 1; k <= 4; k++) {
+        if (c->need_low[k].lo < c->own_low[k].lo) {
+            if (c->prev0 < 0 || c->need_low[k].lo < (c->prev0 >> k))
+                return fail(c, MEAO_ERR_UNSUPPORTED, "halo of level %d reaches beyond the band above", k);
+        }
+        if (c->need_low[k].hi > c->own_low[k].hi) {
+            if (c->next1 < 0 || c->need_low[k].hi > ((c->next1 + (1 << k) - 1) >> k))
+                return fail(c, MEAO_ERR_UNSUPPORTED, "halo of level %d reaches beyond the band below", k);
+        }
+    }
+    return 0;
+}
+
+int allocate(MeaoCtx *c)
+{
+    const int W = c->W, H = c->H;
+    for (int l = 0; l < 7; l++) {                         // AO.cs:276-281
+        const int div = 1 << l;
+        c->lw[l] = (W + div - 1) / div;
+        c->lh[l] = (H + div - 1) / div;
+    }
+    c->band0 = 0; c->band1 = H; c->prev0 = -1; c->next1 = -1;
+    c->plan_dirty = true;
+    if (c->plan_only) return setup_band(c);
+    free_buffers(c);
+    // pitches: rows start on 128-byte boundaries
+    c->lin_pitch = align_up(c->lw[0], 64);
+    c->result_pitch = align_up(c->lw[0], 128);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    size_t o_lin = take((size_t)c->lin_pitch * c->lh[0] * sizeof(__half));
+    size_t o_res = take((size_t)c->result_pitch * c->lh[0]);
+    size_t o_low[5], o_occ[5], o_comb[4];
+    for (int k = 1; k <= 4; k++) {
+        c->low_pitch[k] = align_up(c->lw[k], 32);
+        c->occ_pitch[k] = align_up(c->lw[k], 128);
+        o_low[k] = take((size_t)c->low_pitch[k] * c->lh[k] * sizeof(float));
+        o_occ[k] = take((size_t)c->occ_pitch[k] * c->lh[k]);
+        if (k <= 3) o_comb[k] = take((size_t)c->occ_pitch[k] * c->lh[k]);
+    }
+    size_t o_dst = take((size_t)W * H * sizeof(float));
+    size_t o_ast = take((size_t)W * H);
+    cudaError_t e = cudaMalloc(&c->arena, off);
+    if (e != cudaSuccess) return fail(c, e == cudaErrorMemoryAllocation ? MEAO_ERR_NOMEM : MEAO_ERR_CUDA,
+                                      "cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(e));
+    c->arena_bytes = off;
+    CUDA_TRY(c, cudaMemsetAsync(c->arena, 0, off, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    char *b = (char *)c->arena;
+    c->lin = (__half *)(b + o_lin);
+    c->result = (uint8_t *)(b + o_res);
+    for (int k = 1; k <= 4; k++) {
+        c->low[k] = (float *)(b + o_low[k]);
+        c->occ[k] = (uint8_t *)(b + o_occ[k]);
+        if (k <= 3) c->comb[k] = (uint8_t *)(b + o_comb[k]);
+    }
+    c->depth_stage = (float *)(b + o_dst);
+    c->ao_stage = (uint8_t *)(b + o_ast);
+
+    c->tma_ok = false;
+    if (c->encode) {
+        bool ok = true;
+        for (int k = 1; k <= 4 && ok; k++) {
+            ok &= make_map(c, &c->map_low_ren[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], kRenderBoxW, kRenderBoxH) == 0;
+            ok &= make_map(c, &c->map_low_ups[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], kUpsDepthBoxW, kUpsDepthBoxH) == 0;
+            uint8_t *ao = (k == 4) ? c->occ[4] : c->comb[k];
+            ok &= make_map(c, &c->map_ao_ups[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ao, c->lw[k], c->lh[k], c->occ_pitch[k], kUpsAoBoxW, kUpsAoBoxH) == 0;
+        }
+        c->tma_ok = ok;
+    }
+    if (!c->tma_ok) {
+        memset(c->map_low_ren, 0, sizeof c->map_low_ren);
+        memset(c->map_low_ups, 0, sizeof c->map_low_ups);
+        memset(c->map_ao_ups, 0, sizeof c->map_ao_ups);
+    }
+    return setup_band(c);
+}
+
+int ensure_ready(MeaoCtx *c)
+{
+    if (!c) return MEAO_ERR_INVALID;
+    if (c->W <= 0) return fail(c, MEAO_ERR_INVALID, "meao_resize has not been called");
+    if (c->plan_only) return fail(c, MEAO_ERR_CUDA, "plan-only context (device < 0): no CUDA device bound, and libmeao has no CPU fallback");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->plan_dirty) { build_plan(c); drop_graph(c); }
+    return 0;
+}
+
+// ---- the three recorders ---------------------------------------------------------------------
+
+// PushDownsampleCommands, AO.cs:604-658
+int record_downsample(MeaoCtx *c, const void *depth, int kind, cudaStream_t s)
+{
+    PrepareArgs a{};
+    a.depth = (const float *)depth;
+    a.W = c->W; a.H = c->H;
+    a.depth_row0 = c->band0;
+    a.row0 = c->band0; a.row1 = c->band1;
+    a.lin = c->lin; a.lin_pitch = c->lin_pitch;
+    for (int k = 1; k <= 4; k++) { a.low[k - 1] = c->low[k]; a.low_pitch[k - 1] = c->low_pitch[k]; }
+    a.zbx = c->plan.zb[0]; a.zby = c->plan.zb[1];
+    a.raw = (kind == MEAO_DEPTH_RAW_F32);
+    a.reversed_z = c->camera.reversed_z;
+    a.vec_ok = (((uintptr_t)depth & 15) == 0) && (c->W % 4 == 0);
+    c->last_kind = kind;
+    CUDA_TRY(c, launch_prepare_depth(a, s));
+    c->launches++;
+    return 0;
+}
+
+// PushRenderCommands, AO.cs:660-748
+int record_render(MeaoCtx *c, int k, int kind, cudaStream_t s)
+{
+    static const int idx[7] = {1, 3, 4, 8, 11, 6, 10};       // Render.compute:162-168 table slots
+    RenderArgs a{};
+    a.low = c->low[k]; a.lw = c->lw[k]; a.lh = c->lh[k]; a.lpitch = c->low_pitch[k];
+    a.occ = c->occ[k]; a.opitch = c->occ_pitch[k];
+    a.sw = c->lw[k + 2]; a.sh = c->lh[k + 2];
+    a.pad = host_f16_round((kind == MEAO_DEPTH_RAW_F32) ? c->plan.pad[k] : 0.0f);
+    for (int i = 0; i < 7; i++) {
+        a.inv_thickness[i] = c->plan.inv_thickness[k][idx[i]];
+        a.neg_front[i] = -(a.inv_thickness[i] - 0.5f);                                               // Render.compute:85
+        a.weight[i] = c->plan.sample_weight[k][idx[i]];
+    }
+    a.reject_fadeoff = c->plan.reject_fadeoff;
+    a.intensity = c->plan.intensity;
+    a.row0 = c->need_c[k].lo; a.row1 = c->need_c[k].hi;
+    CUDA_TRY(c, launch_render_ao(c->map_low_ren[k], c->tma_ok, a, s));
+    c->launches++;
+    return 0;
+}
+
+// PushUpsampleCommands with the wiring of AO.cs:528-531
+int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
+{
+    const int hi = lo - 1;
+    UpsampleArgs a{};
+    a.lo_depth = c->low[lo]; a.low = c->lw[lo]; a.loh = c->lh[lo]; a.lo_dpitch = c->low_pitch[lo];
+    a.lo_ao = (lo == 4) ? c->occ[4] : c->comb[lo]; a.lo_apitch = c->occ_pitch[lo];
+    if (hi == 0) { a.hi_depth = c->lin; a.hi_is_half = 1; a.hi_dpitch = c->lin_pitch; a.hi_ao = nullptr; a.hi_apitch = 0; }
+    else { a.hi_depth = c->low[hi]; a.hi_is_half = 0; a.hi_dpitch = c->low_pitch[hi]; a.hi_ao = c->occ[hi]; a.hi_apitch = c->occ_pitch[hi]; }
+    if (hi == 0) {
+        if (ao_out) { a.out = (uint8_t *)ao_out; a.out_pitch = c->W; a.out_row_origin = c->band0; }
+        else { a.out = c->result; a.out_pitch = c->result_pitch; a.out_row_origin = 0; }
+    } else { a.out = c->comb[hi]; a.out_pitch = c->occ_pitch[hi]; a.out_row_origin = 0; }
+    a.out_vec_ok = (((uintptr_t)a.out & 7) == 0) && (a.out_pitch % 8 == 0);
+    a.hiw = c->lw[hi]; a.hih = c->lh[hi];
+    a.noise_filter_strength = c->plan.noise_filter_strength[lo];
+    a.step_size = c->plan.step_size[lo];
+    a.blur_tolerance = c->plan.blur_tolerance[lo];
+    a.upsample_tolerance = c->plan.upsample_tolerance[lo];
+    a.row0 = c->need_c[hi].lo; a.row1 = c->need_c[hi].hi;
+    CUDA_TRY(c, launch_blur_upsample(c->map_low_ups[lo], c->map_ao_ups[lo], c->tma_ok, a, s));
+    c->launches++;
+    return 0;
+}
+
+// record order of RebuildCommandBuffers, AO.cs:511-531
+int record_frame(MeaoCtx *c, const void *depth, int kind, void *ao_out, cudaStream_t s, bool profile)
+{
+    static const char *names[10] = {"prepare_depth", "render_ao L1", "render_ao L2", "render_ao L3", "render_ao L4",
+                                    "blur_upsample L4->L3", "blur_upsample L3->L2", "blur_upsample L2->L1", "blur_upsample L1->L0", ""};
+    std::vector<cudaEvent_t> ev;
+    auto mark = [&]() { if (profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back(e); } };
+    int rc;
+    mark();
+    if ((rc = record_downsample(c, depth, kind, s))) return rc;
+    mark();
+    for (int k = 1; k <= 4; k++) { if ((rc = record_render(c, k, kind, s))) return rc; mark(); }
+    for (int lo = 4; lo >= 1; lo--) { if ((rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s))) return rc; mark(); }
+    if (profile) {
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+        c->last_profile.clear();
+        for (size_t i = 0; i + 1 < ev.size(); i++) {
+            float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            c->last_profile.push_back({names[i], ms});
+        }
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+    return 0;
+}
+
+int buffer_info(const MeaoCtx *c, int id, int *lvl, int *slices, int *elem)
+{
+    if (id == 1) { *lvl = 0; *slices = 1; *elem = 2; }
+    else if (id >= 2 && id <= 5) { *lvl = id - 1; *slices = 1; *elem = 4; }
+    else if (id >= 6 && id <= 9) { *lvl = id - 5 + 2; *slices = 16; *elem = 2; }
+    else if (id >= 10 && id <= 13) { *lvl = id - 9; *slices = 1; *elem = 1; }
+    else if (id >= 14 && id <= 16) { *lvl = id - 13; *slices = 1; *elem = 1; }
+    else if (id == 17) { *lvl = 0; *slices = 1; *elem = 1; }
+    else return -1;
+    (void)c;
+    return 0;
+}
+
+// device pointer + pitch (bytes) of a non-tiled buffer
+int buffer_ptr(MeaoCtx *c, int id, void **p, size_t *pitch_bytes)
+{
+    if (id == 1) { *p = c->lin; *pitch_bytes = (size_t)c->lin_pitch * 2; }
+    else if (id >= 2 && id <= 5) { *p = c->low[id - 1]; *pitch_bytes = (size_t)c->low_pitch[id - 1] * 4; }
+    else if (id >= 10 && id <= 13) { *p = c->occ[id - 9]; *pitch_bytes = c->occ_pitch[id - 9]; }
+    else if (id >= 14 && id <= 16) { *p = c->comb[id - 13]; *pitch_bytes = c->occ_pitch[id - 13]; }
+    else if (id == 17) { *p = c->result; *pitch_bytes = c->result_pitch; }
+    else return -1;
+    return 0;
+}
+
+std::mutex g_event_mutex;
+struct EventBinding { MeaoCtx *ctx; const void *depth; int kind; void *out; };
+std::map<int, EventBinding> g_events;
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int meao_abi_version(void) { return MEAO_ABI_VERSION; }
+
+void meao_default_params(MeaoParams *p)
+{
+    if (!p) return;
+    p->noise_filter_tolerance = 0.0f;   // AO.cs:20
+    p->blur_tolerance = -4.6f;          // AO.cs:28
+    p->upsample_tolerance = -12.0f;     // AO.cs:36
+    p->thickness_modifier = 1.0f;       // AO.cs:44
+    p->intensity = 1.0f;                // AO.cs:52
+    p->debug = 0;                       // AO.cs:60
+    p->ambient_only = 1;                // AO.cs:68
+}
+
+int meao_create(const MeaoDeviceCfg *cfg, MeaoCtx **out)
+{
+    if (!out) return fail(nullptr, MEAO_ERR_INVALID, "out_ctx is NULL");
+    *out = nullptr;
+    if (cfg && cfg->device < 0) {       // host-side planner only: constants, geometry, band/halo ranges
+        MeaoCtx *c = new MeaoCtx();
+        c->device = -1; c->plan_only = true; c->flags = cfg->flags;
+        meao_default_params(&c->params);
+        c->camera = MeaoCamera{0.3f, 1000.0f, 1.0f, 1};
+        *out = c;
+        return MEAO_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MEAO_ERR_CUDA, "no CUDA device available (%s); libmeao has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    const int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= ndev) return fail(nullptr, MEAO_ERR_INVALID, "device %d out of range (0..%d)", dev, ndev - 1);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return fail(nullptr, MEAO_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, MEAO_ERR_CUDA, "device %d is sm_%d%d; libmeao is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+    e = cudaSetDevice(dev);
+    if (e != cudaSuccess) return fail(nullptr, MEAO_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    MeaoCtx *c = new MeaoCtx();
+    c->device = dev;
+    c->flags = cfg ? cfg->flags : 0;
+    meao_default_params(&c->params);
+    c->camera = MeaoCamera{0.3f, 1000.0f, 1.0f, 1};
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(nullptr, MEAO_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+        c->encode = (PFN_encodeTiled)fn;
+    cudaGetLastError();
+    *out = c;
+    return MEAO_OK;
+}
+
+void meao_destroy(MeaoCtx *c)
+{
+    if (!c) return;
+    {
+        std::lock_guard<std::mutex> g(g_event_mutex);
+        for (auto it = g_events.begin(); it != g_events.end();) { if (it->second.ctx == c) it = g_events.erase(it); else ++it; }
+    }
+    if (c->plan_only) { delete c; return; }
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    free_buffers(c);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *meao_last_error(const MeaoCtx *c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+
+int meao_set_params(MeaoCtx *c, const MeaoParams *p)
+{
+    if (!c || !p) return MEAO_ERR_INVALID;
+    // CheckPropertiesChanged, AO.cs:104-113 (ambient_only is not part of the change detection there either)
+    bool changed = c->params.noise_filter_tolerance != p->noise_filter_tolerance || c->params.blur_tolerance != p->blur_tolerance ||
+                   c->params.upsample_tolerance != p->upsample_tolerance || c->params.thickness_modifier != p->thickness_modifier ||
+                   c->params.intensity != p->intensity || c->params.debug != p->debug;
+    if (!(p->thickness_modifier > 0.0f)) return fail(c, MEAO_ERR_INVALID, "thickness_modifier must be > 0");
+    c->params = *p;
+    if (changed) c->plan_dirty = true;
+    return changed ? 1 : 0;
+}
+
+int meao_get_params(const MeaoCtx *c, MeaoParams *out)
+{
+    if (!c || !out) return MEAO_ERR_INVALID;
+    *out = c->params;
+    return MEAO_OK;
+}
+
+int meao_set_camera(MeaoCtx *c, const MeaoCamera *cam)
+{
+    if (!c || !cam) return MEAO_ERR_INVALID;
+    if (!(cam->near_clip > 0) || !(cam->far_clip > cam->near_clip) || !(cam->tan_half_fov_h > 0))
+        return fail(c, MEAO_ERR_INVALID, "bad camera (near %g far %g tanHalfFovH %g)", cam->near_clip, cam->far_clip, cam->tan_half_fov_h);
+    if (memcmp(&c->camera, cam, sizeof *cam) != 0) { c->camera = *cam; c->plan_dirty = true; }
+    return MEAO_OK;
+}
+
+int meao_resize(MeaoCtx *c, int32_t w, int32_t h)
+{
+    if (!c) return MEAO_ERR_INVALID;
+    if (w <= 0 || h <= 0 || w > 32768 || h > 32768) return fail(c, MEAO_ERR_INVALID, "bad size %dx%d", w, h);
+    if (w == c->W && h == c->H && (c->arena || c->plan_only)) return 0;       // RTHandle.CheckBaseDimensions, AO.cs:145-148
+    if (!c->plan_only) {
+        CUDA_TRY(c, cudaSetDevice(c->device));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    c->W = w; c->H = h;
+    int rc = allocate(c);
+    if (rc) { c->W = c->H = 0; return rc; }
+    return 1;
+}
+
+int meao_set_row_band(MeaoCtx *c, int32_t row0, int32_t row1, int32_t prev_row0, int32_t next_row1)
+{
+    if (!c || c->W <= 0) return MEAO_ERR_INVALID;
+    if (row0 < 0 || row1 > c->H || row0 >= row1 || (row0 % 16) || ((row1 % 16) && row1 != c->H))
+        return fail(c, MEAO_ERR_INVALID, "band [%d,%d) must be 16-row aligned inside [0,%d)", row0, row1, c->H);
+    if ((prev_row0 >= 0 && (prev_row0 % 16 || prev_row0 >= row0)) || (next_row1 >= 0 && (next_row1 <= row1 || next_row1 > c->H)))
+        return fail(c, MEAO_ERR_INVALID, "bad neighbour extents");
+    if ((row0 > 0) != (prev_row0 >= 0) || (row1 < c->H) != (next_row1 >= 0))
+        return fail(c, MEAO_ERR_INVALID, "neighbour extents must be given exactly where the band is interior");
+    c->band0 = row0; c->band1 = row1; c->prev0 = prev_row0; c->next1 = next_row1;
+    drop_graph(c);
+    return setup_band(c);
+}
+
+static void halo_ranges(MeaoCtx *c, int side, bool send, Range out[5])
+{
+    // send up:   rows of my own range that the band above needs  = [own.lo, above.need.hi)
+    // recv up:   [need.lo, own.lo)
+    for (int k = 1; k <= 4; k++) out[k] = Range{0, 0};
+    if (side == 0 && c->prev0 < 0) return;
+    if (side == 1 && c->next1 < 0) return;
+    if (!send) {
+        for (int k = 1; k <= 4; k++) {
+            if (side == 0) out[k] = Range{c->need_low[k].lo, c->own_low[k].lo};
+            else out[k] = Range{c->own_low[k].hi, c->need_low[k].hi};
+            if (out[k].hi < out[k].lo) out[k].hi = out[k].lo;
+        }
+        return;
+    }
+    BandNeeds nb = (side == 0) ? compute_needs(c, c->prev0, c->band0) : compute_needs(c, c->band1, c->next1);
+    for (int k = 1; k <= 4; k++) {
+        if (side == 0) out[k] = Range{c->own_low[k].lo, nb.need_low[k].hi};
+        else out[k] = Range{nb.need_low[k].lo, c->own_low[k].hi};
+        if (out[k].hi < out[k].lo) out[k].hi = out[k].lo;
+    }
+}
+
+static int64_t halo_size(MeaoCtx *c, int side, bool send)
+{
+    if (!c || c->W <= 0 || (side != 0 && side != 1)) return MEAO_ERR_INVALID;
+    Range r[5]; halo_ranges(c, side, send, r);
+    int64_t bytes = 0;
+    for (int k = 1; k <= 4; k++) bytes += (int64_t)(r[k].hi - r[k].lo) * c->lw[k] * 4;
+    return bytes;
+}
+int64_t meao_halo_bytes(MeaoCtx *c, int32_t side) { return halo_size(c, side, true); }
+int meao_halo_rows(MeaoCtx *c, int32_t side, int32_t send, int32_t out8[8])
+{
+    if (!c || c->W <= 0 || (side != 0 && side != 1) || !out8) return MEAO_ERR_INVALID;
+    Range r[5]; halo_ranges(c, side, send != 0, r);
+    for (int k = 1; k <= 4; k++) { out8[2 * (k - 1)] = r[k].lo; out8[2 * (k - 1) + 1] = r[k].hi; }
+    return MEAO_OK;
+}
+int meao_band_rows(MeaoCtx *c, int32_t out30[30])
+{
+    if (!c || c->W <= 0 || !out30) return MEAO_ERR_INVALID;
+    for (int k = 0; k <= 4; k++) {
+        out30[2 * k] = c->need_c[k].lo; out30[2 * k + 1] = c->need_c[k].hi;
+        out30[10 + 2 * k] = c->need_low[k].lo; out30[10 + 2 * k + 1] = c->need_low[k].hi;
+        out30[20 + 2 * k] = c->own_low[k].lo; out30[20 + 2 * k + 1] = c->own_low[k].hi;
+    }
+    return MEAO_OK;
+}
+int64_t meao_halo_recv_bytes(MeaoCtx *c, int32_t side) { return halo_size(c, side, false); }
+
+static int halo_copy(MeaoCtx *c, int side, void *packed, bool pack, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (side != 0 && side != 1) return fail(c, MEAO_ERR_INVALID, "side must be 0 or 1");
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    Range r[5]; halo_ranges(c, side, pack, r);
+    char *p = (char *)packed;
+    for (int k = 1; k <= 4; k++) {
+        const int rows = r[k].hi - r[k].lo;
+        if (rows <= 0) continue;
+        const size_t wb = (size_t)c->lw[k] * 4, pb = (size_t)c->low_pitch[k] * 4;
+        char *buf = (char *)(c->low[k] + (size_t)r[k].lo * c->low_pitch[k]);
+        if (pack) CUDA_TRY(c, cudaMemcpy2DAsync(p, wb, buf, pb, wb, rows, cudaMemcpyDeviceToDevice, s));
+        else      CUDA_TRY(c, cudaMemcpy2DAsync(buf, pb, p, wb, wb, rows, cudaMemcpyDeviceToDevice, s));
+        p += wb * rows;
+    }
+    return MEAO_OK;
+}
+int meao_halo_pack(MeaoCtx *c, int32_t side, void *packed, void *stream) { return halo_copy(c, side, packed, true, stream); }
+int meao_halo_unpack(MeaoCtx *c, int32_t side, const void *packed, void *stream) { return halo_copy(c, side, (void *)packed, false, stream); }
+
+int meao_render_band_prepare(MeaoCtx *c, const void *depth, int32_t kind, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!depth) return fail(c, MEAO_ERR_INVALID, "depth is NULL");
+    return record_downsample(c, depth, kind, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int meao_render_band_finish(MeaoCtx *c, void *ao_out, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    const int kind = c->last_kind;
+    for (int k = 1; k <= 4; k++) if ((rc = record_render(c, k, kind, s))) return rc;
+    for (int lo = 4; lo >= 1; lo--) if ((rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s))) return rc;
+    return MEAO_OK;
+}
+
+int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!depth || !ao_out) return fail(c, MEAO_ERR_INVALID, "depth / ao_out is NULL");
+    if (kind != MEAO_DEPTH_RAW_F32 && kind != MEAO_DEPTH_LINEAR_F32) return fail(c, MEAO_ERR_INVALID, "bad depth kind %d", kind);
+    if (c->need_low[1].lo < c->own_low[1].lo || c->need_low[1].hi > c->own_low[1].hi)
+        return fail(c, MEAO_ERR_INVALID, "interior row band: use meao_render_band_prepare / halo exchange / meao_render_band_finish");
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    if (c->flags & MEAO_FLAG_NO_GRAPH) return record_frame(c, depth, kind, ao_out, s, false);
+
+    // plan-once / replay: one captured graph per (depth, out, kind); re-captured when they change
+    if (!c->graph_exec || c->graph_depth != depth || c->graph_out != ao_out || c->graph_kind != kind) {
+        drop_graph(c);
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = c->launches;
+        rc = record_frame(c, depth, kind, ao_out, c->stream, false);
+        c->launches = before;
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { c->graph_exec = nullptr; return fail(c, MEAO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+        c->graph_depth = depth; c->graph_out = ao_out; c->graph_kind = kind;
+    }
+    CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, s));
+    c->launches += meao_kernels_per_frame(c);
+    return MEAO_OK;
+}
+
+int meao_render_host(MeaoCtx *c, const float *depth_host, int32_t kind, uint8_t *ao_host)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!depth_host || !ao_host) return fail(c, MEAO_ERR_INVALID, "depth / ao_out is NULL");
+    const size_t rows = (size_t)(c->band1 - c->band0);
+    CUDA_TRY(c, cudaMemcpyAsync(c->depth_stage, depth_host, rows * c->W * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = meao_render(c, c->depth_stage, kind, c->ao_stage, c->stream))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(ao_host, c->ao_stage, rows * c->W, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MEAO_OK;
+}
+
+int meao_synchronize(MeaoCtx *c)
+{
+    if (!c) return MEAO_ERR_INVALID;
+    if (c->plan_only) return MEAO_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MEAO_OK;
+}
+
+void *meao_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void meao_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int meao_stage_downsample(MeaoCtx *c, const void *depth, int32_t kind, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!depth) return fail(c, MEAO_ERR_INVALID, "depth is NULL");
+    return record_downsample(c, depth, kind, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int meao_stage_render(MeaoCtx *c, int32_t level, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (level < 1 || level > 4) return fail(c, MEAO_ERR_INVALID, "render level %d not in 1..4", level);
+    return record_render(c, level, c->last_kind, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int meao_stage_upsample(MeaoCtx *c, int32_t lo_level, void *ao_out, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (lo_level < 1 || lo_level > 4) return fail(c, MEAO_ERR_INVALID, "upsample lo level %d not in 1..4", lo_level);
+    return record_upsample(c, lo_level, lo_level == 1 ? ao_out : nullptr, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int meao_buffer_desc(const MeaoCtx *c, int32_t id, MeaoBufferDesc *out)
+{
+    if (!c || !out || c->W <= 0) return MEAO_ERR_INVALID;
+    int lvl, slices, elem;
+    if (buffer_info(c, id, &lvl, &slices, &elem)) return MEAO_ERR_INVALID;
+    out->width = c->lw[lvl]; out->height = c->lh[lvl]; out->slices = slices; out->elem_bytes = elem;
+    return MEAO_OK;
+}
+
+int meao_get_buffer(MeaoCtx *c, int32_t id, void *host_out, size_t host_bytes)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    int lvl, slices, elem;
+    if (!host_out || buffer_info(c, id, &lvl, &slices, &elem)) return fail(c, MEAO_ERR_INVALID, "bad buffer id %d", id);
+    const size_t need = (size_t)c->lw[lvl] * c->lh[lvl] * slices * elem;
+    if (host_bytes < need) return fail(c, MEAO_ERR_INVALID, "buffer %d needs %zu bytes, got %zu", id, need, host_bytes);
+    if (slices == 16) {
+        const int k = id - 5;
+        __half *tmp = nullptr;
+        CUDA_TRY(c, cudaMalloc(&tmp, need));
+        const float pad = host_f16_round((c->last_kind == MEAO_DEPTH_RAW_F32) ? c->plan.pad[k] : 0.0f);
+        cudaError_t e = launch_synth_tiled(c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], c->lw[k + 2], c->lh[k + 2], pad, tmp, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, tmp, need, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "tiled view: %s", cudaGetErrorString(e));
+        return MEAO_OK;
+    }
+    void *p; size_t pitch;
+    buffer_ptr(c, id, &p, &pitch);
+    const size_t wb = (size_t)c->lw[lvl] * elem;
+    CUDA_TRY(c, cudaMemcpy2DAsync(host_out, wb, p, pitch, wb, c->lh[lvl], cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MEAO_OK;
+}
+
+int meao_set_buffer(MeaoCtx *c, int32_t id, const void *host_in, size_t host_bytes)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    int lvl, slices, elem;
+    if (!host_in || buffer_info(c, id, &lvl, &slices, &elem) || slices != 1)
+        return fail(c, MEAO_ERR_INVALID, "buffer id %d cannot be set", id);
+    const size_t need = (size_t)c->lw[lvl] * c->lh[lvl] * elem;
+    if (host_bytes < need) return fail(c, MEAO_ERR_INVALID, "buffer %d needs %zu bytes, got %zu", id, need, host_bytes);
+    void *p; size_t pitch;
+    buffer_ptr(c, id, &p, &pitch);
+    const size_t wb = (size_t)c->lw[lvl] * elem;
+    CUDA_TRY(c, cudaMemcpy2DAsync(p, pitch, host_in, wb, wb, c->lh[lvl], cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MEAO_OK;
+}
+
+// The constant getters work without a device context being current: they only need the plan.
+static int plan_only(MeaoCtx *c)
+{
+    if (!c || c->W <= 0) return MEAO_ERR_INVALID;
+    if (c->plan_dirty) { build_plan(c); drop_graph(c); }
+    return 0;
+}
+
+int meao_render_constants(MeaoCtx *c, int32_t level, float out[28])
+{
+    if (plan_only(c) || !out || level < 1 || level > 4) return MEAO_ERR_INVALID;
+    memcpy(out, c->plan.inv_thickness[level], 48);
+    memcpy(out + 12, c->plan.sample_weight[level], 48);
+    out[24] = c->plan.inv_slice_dim[level][0]; out[25] = c->plan.inv_slice_dim[level][1];
+    out[26] = c->plan.reject_fadeoff; out[27] = c->plan.intensity;
+    return MEAO_OK;
+}
+
+int meao_upsample_constants(MeaoCtx *c, int32_t lo, float out[8])
+{
+    if (plan_only(c) || !out || lo < 1 || lo > 4) return MEAO_ERR_INVALID;
+    out[0] = c->plan.inv_low[lo][0]; out[1] = c->plan.inv_low[lo][1];
+    out[2] = c->plan.inv_high[lo][0]; out[3] = c->plan.inv_high[lo][1];
+    out[4] = c->plan.noise_filter_strength[lo]; out[5] = c->plan.step_size[lo];
+    out[6] = c->plan.blur_tolerance[lo]; out[7] = c->plan.upsample_tolerance[lo];
+    return MEAO_OK;
+}
+
+int meao_zbuffer_params(MeaoCtx *c, float out[4])
+{
+    if (plan_only(c) || !out) return MEAO_ERR_INVALID;
+    memcpy(out, c->plan.zb, 16);
+    return MEAO_OK;
+}
+
+int meao_bind_event(MeaoCtx *c, int32_t event_id, const void *depth, int32_t kind, void *ao_out)
+{
+    if (!c) return MEAO_ERR_INVALID;
+    std::lock_guard<std::mutex> g(g_event_mutex);
+    if (!depth && !ao_out) { g_events.erase(event_id); return MEAO_OK; }
+    g_events[event_id] = EventBinding{c, depth, kind, ao_out};
+    return MEAO_OK;
+}
+
+void meao_render_event(int event_id)
+{
+    EventBinding b;
+    {
+        std::lock_guard<std::mutex> g(g_event_mutex);
+        auto it = g_events.find(event_id);
+        if (it == g_events.end()) return;
+        b = it->second;
+    }
+    meao_render(b.ctx, b.depth, b.kind, b.out, nullptr);
+}
+
+MeaoRenderEventFunc meao_get_render_event_func(void) { return meao_render_event; }
+
+int64_t meao_launch_count(const MeaoCtx *c) { return c ? c->launches : 0; }
+int meao_kernels_per_frame(const MeaoCtx *) { return 9; }
+
+int64_t meao_algorithmic_bytes(const MeaoCtx *c, int32_t stage)
+{
+    if (!c || c->W <= 0) return MEAO_ERR_INVALID;
+    auto px = [&](int l) { return (int64_t)c->lw[l] * c->lh[l]; };
+    // every buffer of the reference data-flow read once per consuming stage, written once
+    const int64_t ds1 = 6 * px(0) + 4 * px(1) + 4 * px(2) + 32 * px(3) + 32 * px(4);
+    const int64_t ds2 = 4 * px(2) + 4 * px(3) + 4 * px(4) + 32 * px(5) + 32 * px(6);
+    int64_t ren = 0, ups = 0, ups_final = 0;
+    for (int k = 1; k <= 4; k++) ren += 32 * px(k + 2) + px(k);
+    for (int lo = 4; lo >= 1; lo--) {
+        const int hi = lo - 1;
+        const int64_t b = 5 * px(lo) + (hi == 0 ? 2 : 5) * px(hi) + px(hi);
+        ups += b;
+        if (lo == 1) ups_final = b;
+    }
+    switch (stage) {
+        case 0: return ds1 + ds2 + ren + ups;
+        case 1: return ds1;
+        case 2: return ds2;
+        case 3: return ren;
+        case 4: return ups;
+        case 5: return ups_final;
+        default: return MEAO_ERR_INVALID;
+    }
+}
+
+int meao_profile_frame(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, float *ms_out, const char **names_out, int32_t capacity)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!depth || !ao_out) return fail(c, MEAO_ERR_INVALID, "depth / ao_out is NULL");
+    if ((rc = record_frame(c, depth, kind, ao_out, c->stream, true))) return rc;
+    const int n = (int)c->last_profile.size();
+    for (int i = 0; i < n && i < capacity; i++) {
+        if (ms_out) ms_out[i] = c->last_profile[i].second;
+        if (names_out) names_out[i] = c->last_profile[i].first.c_str();
+    }
+    return n;
+}
+
+}  // extern "C"

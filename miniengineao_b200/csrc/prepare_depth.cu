@@ -1,0 +1,124 @@
+// prepare_depth.cu -- stage 1 of the SSAO pipe: depth linearise + point-sampled mip hierarchy.
+//
+// Replaces Downsample1.compute (Linearize :37-48, main :52-81) and Downsample2.compute (main
+// :32-51) with ONE streaming pass:   raw depth (f32, L0)  ->  LinearDepth (f16, L0),
+// LowDepth1..4 (f32; LowDepth<k>(i,j) = lin(2^k i, 2^k j), a pure point sample -- DS1:64-66,
+// DS2:35).  The deinterleaved f16 atlases are not written (see kernels.h).
+//
+// Bound: HBM.  Algorithmic bytes per L0 pixel: 4 (read) + 2 + 4/4 + 4/16 + 4/64 + 4/256 = 7.33
+// (the reference's Downsample1+2 move 8.24 B/px because they also write and re-read the atlases).
+// There is no data reuse between threads, so no shared-memory staging: each thread streams
+// 2 x 8 pixels with 128-bit loads (L1::no_allocate) and 128-bit stores.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace meao {
+
+namespace {
+
+constexpr int kPrepThreads = 256;
+constexpr int kPrepTileW = 256;   // 32 lanes x 8 pixels
+constexpr int kPrepTileH = 16;    // 8 warps x 2 rows (w, w+8): one LowDepth4 row per tile
+
+template <bool RAW, bool REVERSED>
+__device__ __forceinline__ float linearize(float depth, float zbx, float zby)
+{
+    if (!RAW) return depth;
+    float dist = 1.0f / fmaf(zbx, depth, zby);          // DS1:40 (mad + IEEE reciprocal)
+    if (REVERSED) { if (depth == 0.0f) dist = 1e5f; }   // DS1:41-42
+    else          { if (depth == 1.0f) dist = 1e5f; }   // DS1:43-44
+    return dist;
+}
+
+template <bool RAW, bool REVERSED>
+__global__ void __launch_bounds__(kPrepThreads) prepare_depth_kernel(const PrepareArgs a)
+{
+#ifdef MEAO_DEVICE_OK
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * kPrepTileW + lane * 8;
+    const int ybase = a.row0 + blockIdx.y * kPrepTileH;
+    if (x >= a.W) return;
+    const bool full = a.vec_ok && (x + 8 <= a.W);
+
+    float v[2][8];
+    bool rowok[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        const int y = ybase + warp + 8 * p;
+        rowok[p] = y < a.row1;
+        if (rowok[p]) {
+            const float *src = a.depth + (size_t)(y - a.depth_row0) * a.W + x;
+            if (full) {
+                float4 q0 = ldg_stream_f4(src), q1 = ldg_stream_f4(src + 4);
+                v[p][0] = q0.x; v[p][1] = q0.y; v[p][2] = q0.z; v[p][3] = q0.w;
+                v[p][4] = q1.x; v[p][5] = q1.y; v[p][6] = q1.z; v[p][7] = q1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[p][e] = (x + e < a.W) ? __ldg(src + e) : 0.0f;
+            }
+        }
+    }
+
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        if (!rowok[p]) continue;
+        const int y = ybase + warp + 8 * p;
+        float d[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) d[e] = linearize<RAW, REVERSED>(v[p][e], a.zbx, a.zby);
+
+        __half *lin = a.lin + (size_t)y * a.lin_pitch + x;
+        if (full) {
+            __half2 h0 = __floats2half2_rn(d[0], d[1]), h1 = __floats2half2_rn(d[2], d[3]);
+            __half2 h2 = __floats2half2_rn(d[4], d[5]), h3 = __floats2half2_rn(d[6], d[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&h0); pk.y = *reinterpret_cast<uint32_t *>(&h1);
+            pk.z = *reinterpret_cast<uint32_t *>(&h2); pk.w = *reinterpret_cast<uint32_t *>(&h3);
+            *reinterpret_cast<uint4 *>(lin) = pk;                                        // DS1:46
+            if ((y & 1) == 0) {                                                          // DS1:70  DS2x
+                float *l1 = a.low[0] + (size_t)(y >> 1) * a.low_pitch[0] + (x >> 1);
+                *reinterpret_cast<float4 *>(l1) = make_float4(d[0], d[2], d[4], d[6]);
+                if ((y & 3) == 0) {                                                      // DS1:77  DS4x
+                    float *l2 = a.low[1] + (size_t)(y >> 2) * a.low_pitch[1] + (x >> 2);
+                    *reinterpret_cast<float2 *>(l2) = make_float2(d[0], d[4]);
+                    if ((y & 7) == 0) {                                                  // DS2:40  DS8x
+                        a.low[2][(size_t)(y >> 3) * a.low_pitch[2] + (x >> 3)] = d[0];
+                        if ((y & 15) == 0 && (lane & 1) == 0)                            // DS2:48  DS16x
+                            a.low[3][(size_t)(y >> 4) * a.low_pitch[3] + (x >> 4)] = d[0];
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int xx = x + e;
+                if (xx >= a.W) break;
+                lin[e] = __float2half_rn(d[e]);
+#pragma unroll
+                for (int k = 1; k <= 4; k++) {
+                    const int m = (1 << k) - 1;
+                    if ((xx & m) == 0 && (y & m) == 0)
+                        a.low[k - 1][(size_t)(y >> k) * a.low_pitch[k - 1] + (xx >> k)] = d[e];
+                }
+            }
+        }
+    }
+#endif
+}
+
+}  // namespace
+
+cudaError_t launch_prepare_depth(const PrepareArgs &a, cudaStream_t s)
+{
+    if (a.row1 <= a.row0) return cudaSuccess;
+    dim3 grid(ceil_div(a.W, kPrepTileW), ceil_div(a.row1 - a.row0, kPrepTileH));
+    if (a.raw) {
+        if (a.reversed_z) prepare_depth_kernel<true, true><<<grid, kPrepThreads, 0, s>>>(a);
+        else              prepare_depth_kernel<true, false><<<grid, kPrepThreads, 0, s>>>(a);
+    } else {
+        prepare_depth_kernel<false, true><<<grid, kPrepThreads, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace meao

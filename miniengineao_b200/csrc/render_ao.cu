@@ -1,0 +1,213 @@
+// render_ao.cu -- stage 2 of the SSAO pipe: volumetric-obscurance sampling at one mip level.
+//
+// Replaces Render.compute kernel main_interleaved (TestSamplePair :60-75, TestSamples :77-110,
+// MAIN :112-177) for TiledDepth<k> -> Occlusion<k>.
+//
+// Design (not a port): the reference deinterleaves depth into 16 slices so that its sparse taps
+// become unit-stride texture fetches.  Here the level-k depth stays in NATURAL layout: one CTA
+// stages a (64+32) x (32+32) f32 tile of LowDepth<k> in shared memory with a single TMA box load,
+// rounds it to f16 in place (the reference samples an RHalf atlas), and every thread then reads
+// its 36 taps at stride 4 texels -- which, across a warp of consecutive pixels, is unit-stride and
+// bank-conflict free.  A thread owns two horizontally adjacent pixels so each tap is one LDS.64.
+//
+// Virtual atlas semantics that must be preserved: pixel (X,Y) of level k lives in
+// slice (X&3, Y&3) at slice texel (X>>2, Y>>2); a tap (di,dj) reads slice texel
+// (clamp(i+di, 0, sw-1), clamp(j+dj, 0, sh-1)), i.e. natural pixel (4*ci + (X&3), 4*cj + (Y&3)),
+// which is a padding texel (value `pad`) when it lies outside level k.  Tiles whose footprint is
+// entirely inside the level need none of this and take the TMA path; border tiles resolve the
+// clamp/padding per texel with a gather from global memory.
+//
+// Bound: instruction issue (about 250 thread-instructions per output, 2 B + 1 B of HBM traffic).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace meao {
+
+namespace {
+
+constexpr int kTW = 64, kTH = 32;           // outputs per CTA
+constexpr int kAp = 16;                     // apron: 4 slice texels x stride 4
+constexpr int kSW = kTW + 2 * kAp;          // 96  == kRenderBoxW
+constexpr int kSH = kTH + 2 * kAp;          // 64  == kRenderBoxH
+constexpr int kThreads = 256;
+static_assert(kSW == kRenderBoxW && kSH == kRenderBoxH, "TMA box mismatch");
+
+// Render.compute:60-75 for one sample pair; S1/S2 are the two mirrored taps.
+//   clamp(d, p, 1) == max(saturate(d), p) for p in [0,1], including d = NaN/+-inf (HLSL min/max
+//   return the non-NaN operand, saturate(NaN) = 0), so the result is bit-identical.
+__device__ __forceinline__ float pair_eval(float S1, float S2, float inv_range, float neg_front, float rf)
+{
+    const float d1 = fmaf(S1, inv_range, neg_front);            // REN:65
+    const float d2 = fmaf(S2, inv_range, neg_front);            // REN:66
+    const float p1 = __saturatef(__fmul_rn(rf, d1));            // REN:68
+    const float p2 = __saturatef(__fmul_rn(rf, d2));            // REN:69
+    const float c1 = fmaxf(__saturatef(d1), p2);
+    const float c2 = fmaxf(__saturatef(d2), p1);
+    return __saturatef(fmaf(-p1, p2, __fadd_rn(c1, c2)));       // REN:71-74
+}
+
+// two adjacent pixels at once: c points at the (left) centre texel in the smem tile
+template <int DX, int DY>
+__device__ __forceinline__ void pair2(const float *c, float ir0, float ir1, float nf, float rf, float &r0, float &r1)
+{
+    constexpr int OFF = (4 * DY) * kSW + 4 * DX;
+    const float2 s1 = *reinterpret_cast<const float2 *>(c + OFF);
+    const float2 s2 = *reinterpret_cast<const float2 *>(c - OFF);
+    r0 = pair_eval(s1.x, s2.x, ir0, nf, rf);
+    r1 = pair_eval(s1.y, s2.y, ir1, nf, rf);
+}
+
+// Render.compute:87-93 (axial), x = N
+template <int N>
+__device__ __forceinline__ void axial2(const float *c, float inv0, float inv1, float it, float nf, float w, float rf, float &ao0, float &ao1)
+{
+    const float ir0 = __fmul_rn(it, inv0), ir1 = __fmul_rn(it, inv1);     // REN:84
+    float a0, a1, b0, b1;
+    pair2<N, 0>(c, ir0, ir1, nf, rf, a0, a1);
+    pair2<0, N>(c, ir0, ir1, nf, rf, b0, b1);
+    ao0 = fmaf(w, __fmul_rn(0.5f, __fadd_rn(a0, b0)), ao0);
+    ao1 = fmaf(w, __fmul_rn(0.5f, __fadd_rn(a1, b1)), ao1);
+}
+// Render.compute:94-100 (diagonal), x == y == N: offsets x*TILE - x, x*TILE + x
+template <int N>
+__device__ __forceinline__ void diag2(const float *c, float inv0, float inv1, float it, float nf, float w, float rf, float &ao0, float &ao1)
+{
+    const float ir0 = __fmul_rn(it, inv0), ir1 = __fmul_rn(it, inv1);
+    float a0, a1, b0, b1;
+    pair2<-N, N>(c, ir0, ir1, nf, rf, a0, a1);
+    pair2<N, N>(c, ir0, ir1, nf, rf, b0, b1);
+    ao0 = fmaf(w, __fmul_rn(0.5f, __fadd_rn(a0, b0)), ao0);
+    ao1 = fmaf(w, __fmul_rn(0.5f, __fadd_rn(a1, b1)), ao1);
+}
+// Render.compute:101-109 (L-shaped): y*T + x, y*T - x, x*T + y, x*T - y
+template <int X, int Y>
+__device__ __forceinline__ void lshape2(const float *c, float inv0, float inv1, float it, float nf, float w, float rf, float &ao0, float &ao1)
+{
+    const float ir0 = __fmul_rn(it, inv0), ir1 = __fmul_rn(it, inv1);
+    float a0, a1, b0, b1, c0, c1, d0, d1;
+    pair2<X, Y>(c, ir0, ir1, nf, rf, a0, a1);
+    pair2<-X, Y>(c, ir0, ir1, nf, rf, b0, b1);
+    pair2<Y, X>(c, ir0, ir1, nf, rf, c0, c1);
+    pair2<-Y, X>(c, ir0, ir1, nf, rf, d0, d1);
+    const float t0 = __fadd_rn(__fadd_rn(__fadd_rn(a0, b0), c0), d0);
+    const float t1 = __fadd_rn(__fadd_rn(__fadd_rn(a1, b1), c1), d1);
+    ao0 = fmaf(w, __fmul_rn(0.25f, t0), ao0);
+    ao1 = fmaf(w, __fmul_rn(0.25f, t1), ao1);
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a, const int use_tma)
+{
+#ifdef MEAO_DEVICE_OK
+    extern __shared__ __align__(128) float tile[];     // kSW * kSH floats
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int X0 = blockIdx.x * kTW;
+    const int Y0 = (a.row0 & ~3) + blockIdx.y * kTH;
+
+    const bool interior = use_tma && (X0 - kAp >= 0) && (Y0 - kAp >= 0) && (X0 + kTW + kAp <= a.lw) && (Y0 + kTH + kAp <= a.lh);
+
+    if (interior) {
+        // ---- TMA: one 96x64 f32 box, completion on an mbarrier --------------------------------
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&bar, kSW * kSH * (uint32_t)sizeof(float));
+            tma_load_2d(tile, &low_map, X0 - kAp, Y0 - kAp, &bar);
+        }
+        mbar_wait(&bar, 0);
+        // in-place f16 rounding (what the RHalf atlas store of DS1:71 / DS2:41 does)
+        float4 *t4 = reinterpret_cast<float4 *>(tile);
+#pragma unroll
+        for (int i = 0; i < (kSW * kSH / 4) / kThreads; i++) {
+            float4 q = t4[tid + i * kThreads];
+            q.x = f16_round(q.x); q.y = f16_round(q.y); q.z = f16_round(q.z); q.w = f16_round(q.w);
+            t4[tid + i * kThreads] = q;
+        }
+    } else {
+        // ---- border tile: resolve slice-space clamp + atlas padding per texel ------------------
+        for (int idx = tid; idx < kSW * kSH; idx += kThreads) {
+            const int tx = idx % kSW, ty = idx / kSW;
+            const int vx = X0 - kAp + tx, vy = Y0 - kAp + ty;
+            const int sx = 4 * iclamp(vx >> 2, 0, a.sw - 1) + (vx & 3);     // clamp addressing of Gather, REN:123
+            const int sy = 4 * iclamp(vy >> 2, 0, a.sh - 1) + (vy & 3);
+            float v = a.pad;
+            if (sx < a.lw && sy < a.lh) v = f16_round(__ldg(a.low + (size_t)sy * a.lpitch + sx));
+            tile[idx] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- sampling: thread -> pixels (2*lane, 2*lane+1) of rows wy, wy+8, wy+16, wy+24 ------------
+    const int lane = tid & 31, wy = tid >> 5;
+    const int px = 2 * lane;
+    const float rf = a.reject_fadeoff;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        const int row = wy + 8 * i;
+        const int oy = Y0 + row, ox = X0 + px;
+        if (oy < a.row0 || oy >= a.row1 || ox >= a.lw) continue;
+        const float *c = tile + (row + kAp) * kSW + (px + kAp);
+        const float2 ctr = *reinterpret_cast<const float2 *>(c);
+        const float inv0 = 1.0f / ctr.x, inv1 = 1.0f / ctr.y;                // REN:140
+        float ao0 = 0.0f, ao1 = 0.0f;                                        // REN:142
+        // REN:162-168 -- the 36-sample checker pattern, in call order
+        axial2<2>(c, inv0, inv1, a.inv_thickness[0], a.neg_front[0], a.weight[0], rf, ao0, ao1);
+        axial2<4>(c, inv0, inv1, a.inv_thickness[1], a.neg_front[1], a.weight[1], rf, ao0, ao1);
+        diag2<1>(c, inv0, inv1, a.inv_thickness[2], a.neg_front[2], a.weight[2], rf, ao0, ao1);
+        diag2<2>(c, inv0, inv1, a.inv_thickness[3], a.neg_front[3], a.weight[3], rf, ao0, ao1);
+        diag2<3>(c, inv0, inv1, a.inv_thickness[4], a.neg_front[4], a.weight[4], rf, ao0, ao1);
+        lshape2<1, 3>(c, inv0, inv1, a.inv_thickness[5], a.neg_front[5], a.weight[5], rf, ao0, ao1);
+        lshape2<2, 4>(c, inv0, inv1, a.inv_thickness[6], a.neg_front[6], a.weight[6], rf, ao0, ao1);
+        // REN:176  lerp(1, ao, gIntensity) -> R8
+        const uint32_t k0 = unorm8_code(fmaf(a.intensity, __fadd_rn(ao0, -1.0f), 1.0f));
+        const uint32_t k1 = unorm8_code(fmaf(a.intensity, __fadd_rn(ao1, -1.0f), 1.0f));
+        uint8_t *dst = a.occ + (size_t)oy * a.opitch + ox;
+        if (ox + 1 < a.lw) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(k0 | (k1 << 8));
+        else dst[0] = (uint8_t)k0;
+    }
+#endif
+}
+
+// debug view: TiledDepth<k>[slice][j][i] exactly as Downsample1/2 would have written it
+__global__ void synth_tiled_kernel(const float *low, int lw, int lh, int lpitch, int sw, int sh, float pad, __half *out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, s = blockIdx.z;
+    if (i >= sw) return;
+    const int x = 4 * i + (s & 3), y = 4 * j + (s >> 2);                     // inverse of DS1:69,71
+    float v = pad;
+    if (x < lw && y < lh) v = low[(size_t)y * lpitch + x];
+    out[((size_t)s * sh + j) * sw + i] = __float2half_rn(v);
+}
+
+}  // namespace
+
+cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const RenderArgs &a, cudaStream_t s)
+{
+    if (a.row1 <= a.row0) return cudaSuccess;
+    const int ybase = a.row0 & ~3;
+    dim3 grid(ceil_div(a.lw, kTW), ceil_div(a.row1 - ybase, kTH));
+    const size_t smem = (size_t)kSW * kSH * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(render_ao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    render_ao_kernel<<<grid, kThreads, smem, s>>>(low_map, a, use_tma ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int sw, int sh, float pad,
+                               __half *out, cudaStream_t s)
+{
+    dim3 grid(ceil_div(sw, 128), sh, 16);
+    synth_tiled_kernel<<<grid, 128, 0, s>>>(low, lw, lh, lpitch, sw, sh, pad, out);
+    return cudaGetLastError();
+}
+
+}  // namespace meao

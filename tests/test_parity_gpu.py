@@ -1,0 +1,331 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (via the ctypes host), against the
+CPU oracle on identical inputs.  Bar: BIT-EXACT on every buffer (f16 bits, f32 bits, unorm8
+codes) -- north_star's tolerance is 1e-3 absolute on the AO value, and one unorm8 code is 3.9e-3,
+so any differing code would already be out of tolerance (TOL_CODES = 0).
+
+The reference publishes no golden vectors (parity unpinned, see oracle/meao_oracle.h); the oracle
+is pinned by analytic identities and a second independent restatement in tests/test_oracle.py.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_CODES = 0   # allowed |delta| in unorm8 codes; 1e-3 absolute < 1/255
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a GPU"
+    return torch
+
+
+def _mk(W, H, **params):
+    from miniengineao_b200 import AmbientOcclusion, Camera
+    from oracle.oracle import Oracle
+    cam_kw = {}
+    if "reversed_z" in params:
+        cam_kw["usesReversedZBuffer"] = params["reversed_z"]
+    ao = AmbientOcclusion(Camera(W, H, **cam_kw), device=0, use_graph=params.pop("use_graph", True))
+    okw = {}
+    for py, cs in (("noise_filter_tolerance", "noiseFilterTolerance"), ("blur_tolerance", "blurTolerance"),
+                   ("upsample_tolerance", "upsampleTolerance"), ("thickness_modifier", "thicknessModifier"),
+                   ("intensity", "intensity")):
+        if py in params:
+            setattr(ao, cs, params[py])
+            okw[py] = params[py]
+    if "reversed_z" in params:
+        okw["reversed_z"] = params["reversed_z"]
+    orc = Oracle(W, H, threads=8, **okw)
+    return ao, orc
+
+
+def _compare_all(ao, orc, tag):
+    """Every debug buffer 1..17 of the CUDA path against the oracle, bit for bit."""
+    bad = []
+    for bid in range(1, 18):
+        got = ao.debug_buffer(bid)
+        ref = orc.buffer(bid)
+        if got.dtype == np.uint8:
+            refc = orc.codes(bid)
+            n = int((np.abs(got.astype(np.int16) - refc.astype(np.int16)) > TOL_CODES).sum())
+        elif got.dtype == np.float16:
+            n = int((got.view(np.uint16) != ref.astype(np.float16).view(np.uint16)).sum())
+        else:
+            n = int((got.view(np.uint32) != ref.view(np.uint32)).sum())
+        if n:
+            bad.append((bid, ao.DEBUG_NAMES[bid], n, got.size))
+    assert not bad, f"{tag}: mismatching buffers (id, name, #diff, size): {bad}"
+
+
+SIZES = [(256, 256), (64, 64), (16, 16), (8, 8), (1, 1), (3, 5), (130, 70), (250, 131), (321, 203), (640, 360), (1000, 37), (37, 1000)]
+
+
+@pytest.mark.parametrize("W,H", SIZES)
+def test_full_pipe_bit_exact_random(torch_cuda, W, H):
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    ao, orc = _mk(W, H, intensity=1.1)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=W * 7 + H))
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert int((got != ref).sum()) == 0
+    _compare_all(ao, orc, f"{W}x{H}")
+
+
+def test_flat_sphere_256(torch_cuda):
+    """BASELINE.json configs[0]: 256x256 synthetic flat+sphere depth."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    ao, orc = _mk(256, 256)
+    depth = synth.lin01_to_raw(synth.flat_sphere(256, 256))
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert np.array_equal(got, ref)
+    _compare_all(ao, orc, "flat+sphere")
+
+
+@pytest.mark.parametrize("params", [
+    dict(intensity=0.0), dict(intensity=2.0), dict(thickness_modifier=10.0), dict(thickness_modifier=2.5, intensity=1.3),
+    dict(blur_tolerance=-1.0), dict(blur_tolerance=-8.0), dict(upsample_tolerance=-1.0), dict(upsample_tolerance=-6.0, noise_filter_tolerance=-8.0),
+    dict(noise_filter_tolerance=-3.0, blur_tolerance=-3.0, upsample_tolerance=-4.0, thickness_modifier=4.0, intensity=0.7),
+    dict(reversed_z=False),
+])
+def test_parameter_sweep(torch_cuda, params):
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 322, 190
+    ao, orc = _mk(W, H, **params)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=11), reversed_z=params.get("reversed_z", True))
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert np.array_equal(got, ref), params
+    _compare_all(ao, orc, str(params))
+
+
+def test_corridor_1080p(torch_cuda):
+    """BASELINE.json configs[1]: 1920x1080 Sponza-like depth, full multi-scale pipe."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 1920, 1080
+    ao, orc = _mk(W, H, intensity=1.1)
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert int((got != ref).sum()) == 0
+    _compare_all(ao, orc, "1080p corridor")
+
+
+def test_sky_pixels_and_nan_semantics(torch_cuda):
+    """Raw depth 0 (reversed-Z sky) -> 1e5 -> +inf in f16 -> inf*0 = NaN inside the sampler; the HLSL
+    saturate/min/max NaN rules must hold on both sides."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 200, 120
+    ao, orc = _mk(W, H)
+    lin = synth.random_depth(W, H, seed=5)
+    depth = synth.lin01_to_raw(lin)
+    depth[20:60, 30:90] = 0.0           # a sky window
+    depth[::17, ::13] = 0.0             # isolated sky pixels
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert np.array_equal(got, ref)
+    _compare_all(ao, orc, "sky")
+
+
+def test_linear_depth_ingest(torch_cuda):
+    from miniengineao_b200 import synth
+    from oracle.oracle import Oracle
+    from miniengineao_b200 import AmbientOcclusion, Camera
+    torch = torch_cuda
+    W, H = 250, 131
+    lin = synth.random_depth(W, H, seed=9)
+    ao = AmbientOcclusion(Camera(W, H), device=0)
+    orc = Oracle(W, H, depth_is_linear=True)
+    ref = orc.run(lin)
+    got = ao.render(torch.from_numpy(lin).cuda(), linear=True).cpu().numpy()
+    assert np.array_equal(got, ref)
+    _compare_all(ao, orc, "linear ingest")
+
+
+def test_stagewise_with_injected_inputs(torch_cuda):
+    """Each stage alone, fed the ORACLE's inputs (meao_set_buffer), like the reference's debug views."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 330, 170
+    ao, orc = _mk(W, H, intensity=1.2)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=21))
+    orc.run(depth)
+    d = torch.from_numpy(depth).cuda()
+    ao.stage_downsample(d)
+    for bid in (1, 2, 3, 4, 5, 6, 7, 8, 9):
+        got, ref = ao.debug_buffer(bid), orc.buffer(bid)
+        if got.dtype == np.float16:
+            assert np.array_equal(got.view(np.uint16), ref.astype(np.float16).view(np.uint16)), bid
+        else:
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), bid
+    for k in range(1, 5):
+        ao.set_debug_buffer(1 + k, orc.buffer(1 + k))
+        ao.stage_render(k)
+        assert np.array_equal(ao.debug_buffer(9 + k), orc.codes(9 + k)), f"render level {k}"
+    for lo in range(4, 0, -1):
+        hi = lo - 1
+        ao.set_debug_buffer(1 + lo, orc.buffer(1 + lo))
+        ao.set_debug_buffer(13 if lo == 4 else 13 + lo, orc.codes(13 if lo == 4 else 13 + lo))
+        if hi > 0:
+            ao.set_debug_buffer(1 + hi, orc.buffer(1 + hi))
+            ao.set_debug_buffer(9 + hi, orc.codes(9 + hi))
+        else:
+            ao.set_debug_buffer(1, orc.buffer(1).astype(np.float16))
+        ao.stage_upsample(lo)
+        out_id = 17 if hi == 0 else 13 + hi
+        assert np.array_equal(ao.debug_buffer(out_id), orc.codes(out_id)), f"upsample {lo}->{hi}"
+
+
+# ---- size-independent properties at BASELINE.json's full sizes ---------------------------------------
+
+@pytest.mark.parametrize("W,H", [(1920, 1080), (3840, 2160), (7680, 4320)])
+def test_constant_depth_gives_255_everywhere(torch_cuda, W, H):
+    """constant depth => every pair = 1, sum of weights = 1 => code 255 at all levels."""
+    torch = torch_cuda
+    ao, _ = _mk(16, 16)
+    ao.camera.pixelWidth, ao.camera.pixelHeight = W, H
+    d = torch.full((H, W), 0.02, dtype=torch.float32, device="cuda")
+    out = ao.render(d)
+    assert int((out != 255).sum().item()) == 0
+    for bid in range(10, 17):
+        assert int((ao.debug_buffer(bid) != 255).sum()) == 0, bid
+
+
+@pytest.mark.parametrize("W,H", [(3840, 2160)])
+def test_intensity_zero_gives_255(torch_cuda, W, H):
+    """intensity 0 => lerp(1, ao, 0) = 1 for any depth."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    ao, _ = _mk(W, H, intensity=0.0)
+    d = torch.from_numpy(synth.lin01_to_raw(synth.corridor(W, H))).cuda()
+    out = ao.render(d)
+    assert int((out != 255).sum().item()) == 0
+
+
+def test_4k_matches_oracle_on_crops_and_checksum(torch_cuda):
+    """4K (the metric's config): full oracle comparison (the C oracle does 4K in a few seconds with 8 threads)."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 3840, 2160
+    ao, orc = _mk(W, H, intensity=1.1)
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert int((got != ref).sum()) == 0
+    assert int(got.astype(np.uint64).sum()) == int(ref.astype(np.uint64).sum())
+
+
+def test_graph_replay_equals_stream_launch_and_is_deterministic(torch_cuda):
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 1920, 1080
+    depth = torch.from_numpy(synth.lin01_to_raw(synth.corridor(W, H))).cuda()
+    a1, _ = _mk(W, H)
+    a2, _ = _mk(W, H, use_graph=False)
+    o1 = a1.render(depth).clone()
+    o1b = a1.render(depth).clone()       # second call replays the captured graph
+    o2 = a2.render(depth)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o1b) and torch.equal(o1, o2)
+    assert a1.launch_count == 18 and a2.launch_count == 9
+
+
+def test_replan_on_parameter_and_size_change(torch_cuda):
+    """LateUpdate semantics (AO.cs:329-350): rebuild only when a property or the size changed."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    ao, orc = _mk(128, 96)
+    d = torch.from_numpy(synth.lin01_to_raw(synth.random_depth(128, 96, 3))).cuda()
+    ao.render(d)
+    n = ao.rebuild_count
+    ao.render(d)
+    assert ao.rebuild_count == n
+    ao.intensity = 0.5
+    out = ao.render(d).cpu().numpy()
+    assert ao.rebuild_count == n + 1
+    orc.params.intensity = 0.5
+    assert np.array_equal(out, orc.run(d.cpu().numpy()))
+    ao.camera.pixelWidth, ao.camera.pixelHeight = 96, 128
+    d2 = synth.lin01_to_raw(synth.random_depth(96, 128, 4))
+    out2 = ao.render(torch.from_numpy(d2).cuda()).cpu().numpy()
+    assert ao.rebuild_count == n + 2
+    from oracle.oracle import Oracle
+    assert np.array_equal(out2, Oracle(96, 128, intensity=0.5).run(d2))
+
+
+def test_host_buffer_path_and_event_hook(torch_cuda):
+    import ctypes as C
+    from miniengineao_b200 import synth, _native as N
+    torch = torch_cuda
+    W, H = 320, 200
+    ao, orc = _mk(W, H)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, 8))
+    ref = orc.run(depth)
+    assert np.array_equal(ao.render_host(depth), ref)
+    # command-buffer hook: IssuePluginEvent-style callback
+    d = torch.from_numpy(depth).cuda()
+    out = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    lib = N.lib()
+    N.check(ao._ctx, lib.meao_bind_event(ao._ctx, 42, d.data_ptr(), 0, out.data_ptr()))
+    fn = lib.meao_get_render_event_func()
+    fn(42)
+    ao.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("W,H,bands", [(1280, 720, 2), (1920, 1080, 2), (3840, 2160, 4)])
+def test_row_bands_equal_whole_frame(torch_cuda, W, H, bands):
+    """Tile-vs-whole equality: each band context computes its rows from its own depth rows
+    plus the halo rows of LowDepth1..4 packed by its neighbours; the union must be bit-identical to the
+    single-context frame.  All bands live on one GPU here; the exchange is a device copy."""
+    from miniengineao_b200 import AmbientOcclusion, Camera, synth
+    torch = torch_cuda
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    whole = AmbientOcclusion(Camera(W, H), device=0)
+    ref = whole.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    blocks = (H + 15) // 16
+    cuts = [min(H, 16 * ((blocks * i) // bands)) for i in range(bands)] + [H]
+    ctxs = []
+    for i in range(bands):
+        a = AmbientOcclusion(Camera(W, H), device=0)
+        a.set_row_band(cuts[i], cuts[i + 1], cuts[i - 1] if i > 0 else -1, cuts[i + 2] if i + 2 <= bands else -1)
+        ctxs.append(a)
+    dts = [torch.from_numpy(depth[cuts[i]:cuts[i + 1]]).cuda() for i in range(bands)]
+    for a, d in zip(ctxs, dts):
+        a.band_prepare(d)
+    torch.cuda.synchronize()
+    for i in range(bands):
+        for side, j in ((0, i - 1), (1, i + 1)):
+            if j < 0 or j >= bands:
+                continue
+            nbytes = ctxs[i].halo_bytes(side)
+            assert nbytes == ctxs[j].halo_recv_bytes(1 - side)
+            buf = torch.empty(max(nbytes, 4), dtype=torch.uint8, device="cuda")
+            ctxs[i].halo_pack(side, buf)
+            ctxs[i].synchronize()
+            ctxs[j].halo_unpack(1 - side, buf)
+            ctxs[j].synchronize()
+    got = np.zeros((H, W), np.uint8)
+    for i, a in enumerate(ctxs):
+        o = torch.empty((cuts[i + 1] - cuts[i], W), dtype=torch.uint8, device="cuda")
+        a.band_finish(o)
+        a.synchronize()
+        got[cuts[i]:cuts[i + 1]] = o.cpu().numpy()
+    assert int((got != ref).sum()) == 0
+
+
+def test_too_thin_band_is_refused(torch_cuda):
+    """A band thinner than the dependency radius (346 L0 rows for Occlusion4) would need a multi-hop
+    exchange: libmeao refuses it loudly instead of computing garbage."""
+    from miniengineao_b200 import AmbientOcclusion, Camera, MeaoError
+    a = AmbientOcclusion(Camera(1920, 1088), device=0)
+    with pytest.raises(MeaoError) as e:
+        a.set_row_band(272, 544, 0, 816)
+    assert e.value.code == -3
