@@ -117,7 +117,7 @@ int meao_resize(MeaoCtx *ctx, int32_t width, int32_t height);
 /* replaces: replay of the "SSAO" command buffer, steps 1-10 of RebuildCommandBuffers (AO.cs:511-531):
  * Downsample1+2, Render x4, Upsample x4.  depth: device pointer, width*height f32, rows contiguous
  * (row pitch = width*4).  ao_out: device pointer, width*height bytes (R8, AO.cs:475).
- * stream: a cudaStream_t (NULL = the context's own stream).  Asynchronous.  Re-plans first if dirty
+ * stream: a cudaStream_t, used as given (NULL = the CUDA legacy default stream).  Asynchronous.  Re-plans first if dirty
  * (LateUpdate, AO.cs:329-350). */
 int meao_render(MeaoCtx *ctx, const void *depth_dev, int32_t depth_kind, void *ao_out_dev, void *stream);
 /* Same with HOST buffers: H2D copy of depth, the ten passes, D2H copy of the AO texture, then a

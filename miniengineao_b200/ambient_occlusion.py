@@ -128,9 +128,8 @@ class AmbientOcclusion:
             raise ValueError(f"depth shape {tuple(depth.shape)} != {(rows, self._width)}")
         if out is None:
             out = torch.empty((rows, self._width), dtype=torch.uint8, device=depth.device)
-        s = stream if stream is not None else torch.cuda.current_stream(depth.device)
         kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
-        self._check(self._lib.meao_render(self._ctx, depth.data_ptr(), kind, out.data_ptr(), s.cuda_stream))
+        self._check(self._lib.meao_render(self._ctx, depth.data_ptr(), kind, out.data_ptr(), self._stream(stream)))
         return out
 
     def render_host(self, depth: np.ndarray, out: np.ndarray | None = None, *, linear: bool = False) -> np.ndarray:
@@ -147,21 +146,30 @@ class AmbientOcclusion:
         return out
 
     def synchronize(self) -> None:
+        """Wait for the context's own stream (host-buffer path, debug copies) AND the current torch stream."""
         self._check(self._lib.meao_synchronize(self._ctx))
+        import torch
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def _stream(self, stream=None):
+        """cudaStream_t handle to launch on: the given torch stream or torch's current stream."""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return C.c_void_p(s.cuda_stream)
 
     # ---- stage entry points (mirror Push*Commands) -----------------------------------------------
     def stage_downsample(self, depth, *, linear: bool = False) -> None:
         self.LateUpdate()
         kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
-        self._check(self._lib.meao_stage_downsample(self._ctx, depth.data_ptr(), kind, None))
+        self._check(self._lib.meao_stage_downsample(self._ctx, depth.data_ptr(), kind, self._stream()))
 
     def stage_render(self, level: int) -> None:
         self.LateUpdate()
-        self._check(self._lib.meao_stage_render(self._ctx, level, None))
+        self._check(self._lib.meao_stage_render(self._ctx, level, self._stream()))
 
     def stage_upsample(self, lo_level: int) -> None:
         self.LateUpdate()
-        self._check(self._lib.meao_stage_upsample(self._ctx, lo_level, None, None))
+        self._check(self._lib.meao_stage_upsample(self._ctx, lo_level, None, self._stream()))
 
     # ---- debug views (AO.cs:787-820) ---------------------------------------------------------------
     def buffer_desc(self, debug_id: int) -> N.MeaoBufferDesc:
@@ -242,18 +250,17 @@ class AmbientOcclusion:
         return self._check(self._lib.meao_halo_recv_bytes(self._ctx, side))
 
     def halo_pack(self, side: int, buf, stream=None) -> None:
-        self._check(self._lib.meao_halo_pack(self._ctx, side, buf.data_ptr(), stream.cuda_stream if stream else None))
+        self._check(self._lib.meao_halo_pack(self._ctx, side, buf.data_ptr(), self._stream(stream)))
 
     def halo_unpack(self, side: int, buf, stream=None) -> None:
-        self._check(self._lib.meao_halo_unpack(self._ctx, side, buf.data_ptr(), stream.cuda_stream if stream else None))
+        self._check(self._lib.meao_halo_unpack(self._ctx, side, buf.data_ptr(), self._stream(stream)))
 
     def band_prepare(self, depth_band, *, linear: bool = False, stream=None) -> None:
         kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
-        self._check(self._lib.meao_render_band_prepare(self._ctx, depth_band.data_ptr(), kind,
-                                                       stream.cuda_stream if stream else None))
+        self._check(self._lib.meao_render_band_prepare(self._ctx, depth_band.data_ptr(), kind, self._stream(stream)))
 
     def band_finish(self, out_band, stream=None) -> None:
-        self._check(self._lib.meao_render_band_finish(self._ctx, out_band.data_ptr(), stream.cuda_stream if stream else None))
+        self._check(self._lib.meao_render_band_finish(self._ctx, out_band.data_ptr(), self._stream(stream)))
 
     # ---- introspection ----------------------------------------------------------------------------
     @property

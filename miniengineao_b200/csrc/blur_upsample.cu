@@ -29,16 +29,22 @@ namespace {
 
 constexpr int kHW = 64, kHH = 32;               // hi-res outputs per CTA
 constexpr int kRawW = 38, kRawH = 22;           // low-res footprint actually used
-constexpr int kRawP = kUpsDepthBoxW;            // 40: pitch of the raw arrays (== depth box width)
-constexpr int kAoP = kUpsAoBoxW;                // 48: pitch of the raw unorm8 tile (== AO box width)
+constexpr int kRawP = 40;                       // pitch of the raw arrays
+constexpr int kBoxDP = kUpsDepthBoxW;           // 40: depth TMA box width  (box column = raw column + kBoxDOff)
+constexpr int kBoxAP = kUpsAoBoxW;              // 64: AO TMA box width     (box column = raw column + kBoxAOff)
+// MEASURED on B200: cp.async.bulk.tensor (tiled, no swizzle) raises "illegal instruction" unless the
+// innermost start coordinate * element size is a multiple of 16 bytes.  The raw tile starts at low-res
+// column 32*bx - 3, so the boxes start at 32*bx - 4 (f32: 16 B aligned) and 32*bx - 16 (u8).
+constexpr int kBoxDOff = 1, kBoxAOff = 13;
 constexpr int kBlurW = 34, kBlurH = 18;         // blurred texels needed
 constexpr int kBlurP = 36;                      // pitch of the blurred arrays
 constexpr int kThreads = 256;
 static_assert(kRawH == kUpsDepthBoxH && kRawH == kUpsAoBoxH, "TMA box mismatch");
 
 struct __align__(128) Smem {
-    alignas(128) float lo_depth[kRawH * kRawP];     // raw low-res depth (LoResDB), TMA destination
-    alignas(128) uint8_t ao_raw[kRawH * kAoP];      // raw low-res AO codes (LoResAO1), TMA destination
+    alignas(128) float box_depth[kRawH * kBoxDP];   // TMA destination: low-res depth box (LoResDB)
+    alignas(128) uint8_t box_ao[kRawH * kBoxAP];    // TMA destination: low-res AO codes box (LoResAO1)
+    alignas(16) float lo_depth[kRawH * kRawP];      // raw low-res depth, column 0 = virtual column lx0
     alignas(16) float inv_depth[kRawH * kRawP];     // DepthCache, UPS:67-71
     alignas(16) float ao[kRawH * kRawP];            // AOCache1 as loaded, UPS:62-65
     alignas(16) float hblur[kRawH * kBlurP];        // AOCache2, UPS:127-129
@@ -96,15 +102,17 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
         if (tid == 0) { mbar_init(&sm.bar, 1); fence_mbar_init(); }
         __syncthreads();
         if (tid == 0) {
-            mbar_arrive_expect_tx(&sm.bar, (uint32_t)(kRawH * kRawP * sizeof(float) + kRawH * kAoP));
-            tma_load_2d(sm.lo_depth, &lo_depth_map, lx0, ly0, &sm.bar);
-            tma_load_2d(sm.ao_raw, &lo_ao_map, lx0, ly0, &sm.bar);
+            mbar_arrive_expect_tx(&sm.bar, (uint32_t)(kRawH * kBoxDP * sizeof(float) + kRawH * kBoxAP));
+            tma_load_2d(sm.box_depth, &lo_depth_map, lx0 - kBoxDOff, ly0, &sm.bar);
+            tma_load_2d(sm.box_ao, &lo_ao_map, lx0 - kBoxAOff, ly0, &sm.bar);
         }
         mbar_wait(&sm.bar, 0);
         for (int idx = tid; idx < kRawH * kRawP; idx += kThreads) {
             const int r = idx / kRawP, c = idx - r * kRawP;
-            sm.inv_depth[r * kRawP + c] = 1.0f / sm.lo_depth[r * kRawP + c];            // UPS:67
-            sm.ao[r * kRawP + c] = unorm8_load(sm.ao_raw[r * kAoP + c]);
+            const float d = (c + kBoxDOff < kBoxDP) ? sm.box_depth[r * kBoxDP + c + kBoxDOff] : 1.0f;   // column 39 is never consumed
+            sm.lo_depth[r * kRawP + c] = d;
+            sm.inv_depth[r * kRawP + c] = 1.0f / d;                                          // UPS:67
+            sm.ao[r * kRawP + c] = unorm8_load(sm.box_ao[r * kBoxAP + c + kBoxAOff]);
         }
     } else {
         // border tile: point + clamp addressing (UPS:56,67)

@@ -71,7 +71,7 @@ struct UpsampleArgs {
 cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensorMap &lo_ao_map, bool use_tma,
                                  const UpsampleArgs &a, cudaStream_t s);
 constexpr int kUpsDepthBoxW = 40, kUpsDepthBoxH = 22; // TMA boxes of the upsample kernel
-constexpr int kUpsAoBoxW = 48, kUpsAoBoxH = 22;
+constexpr int kUpsAoBoxW = 64, kUpsAoBoxH = 22;
 
 // ---- debug: synthesise a TiledDepth<k> view (reference layout [16][sh][sw], f16 bits) ----------
 cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int sw, int sh, float pad,

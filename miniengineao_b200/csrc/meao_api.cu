@@ -98,6 +98,7 @@ struct MeaoCtx {
     // CUDA graph cache (one entry: last (depth, out, kind, stream-independent))
     cudaGraphExec_t graph_exec = nullptr;
     const void *graph_depth = nullptr; void *graph_out = nullptr; int graph_kind = -1;
+    void *last_out = nullptr;               // where the last final upsample wrote (nullptr: c->result)
     int last_kind = MEAO_DEPTH_RAW_F32;     // ingest kind of the last downsample (selects the atlas padding value)
 
     std::vector<std::pair<std::string, float>> last_profile;
@@ -392,6 +393,7 @@ int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
     if (hi == 0) {
         if (ao_out) { a.out = (uint8_t *)ao_out; a.out_pitch = c->W; a.out_row_origin = c->band0; }
         else { a.out = c->result; a.out_pitch = c->result_pitch; a.out_row_origin = 0; }
+        c->last_out = ao_out;
     } else { a.out = c->comb[hi]; a.out_pitch = c->occ_pitch[hi]; a.out_row_origin = 0; }
     a.out_vec_ok = (((uintptr_t)a.out & 7) == 0) && (a.out_pitch % 8 == 0);
     a.hiw = c->lw[hi]; a.hih = c->lh[hi];
@@ -515,7 +517,9 @@ int meao_create(const MeaoDeviceCfg *cfg, MeaoCtx **out)
     if (e != cudaSuccess) { delete c; return fail(nullptr, MEAO_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+    const char *no_tma = getenv("MEAO_DISABLE_TMA");     // debugging aid: force the gather path in every tile
+    if (!(no_tma && no_tma[0] == '1') &&
+        cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
         c->encode = (PFN_encodeTiled)fn;
     cudaGetLastError();
     *out = c;
@@ -652,7 +656,7 @@ static int halo_copy(MeaoCtx *c, int side, void *packed, bool pack, void *stream
 {
     int rc = ensure_ready(c); if (rc) return rc;
     if (side != 0 && side != 1) return fail(c, MEAO_ERR_INVALID, "side must be 0 or 1");
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     Range r[5]; halo_ranges(c, side, pack, r);
     char *p = (char *)packed;
     for (int k = 1; k <= 4; k++) {
@@ -673,13 +677,13 @@ int meao_render_band_prepare(MeaoCtx *c, const void *depth, int32_t kind, void *
 {
     int rc = ensure_ready(c); if (rc) return rc;
     if (!depth) return fail(c, MEAO_ERR_INVALID, "depth is NULL");
-    return record_downsample(c, depth, kind, stream ? (cudaStream_t)stream : c->stream);
+    return record_downsample(c, depth, kind, (cudaStream_t)stream);
 }
 
 int meao_render_band_finish(MeaoCtx *c, void *ao_out, void *stream)
 {
     int rc = ensure_ready(c); if (rc) return rc;
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     const int kind = c->last_kind;
     for (int k = 1; k <= 4; k++) if ((rc = record_render(c, k, kind, s))) return rc;
     for (int lo = 4; lo >= 1; lo--) if ((rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s))) return rc;
@@ -693,7 +697,7 @@ int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void 
     if (kind != MEAO_DEPTH_RAW_F32 && kind != MEAO_DEPTH_LINEAR_F32) return fail(c, MEAO_ERR_INVALID, "bad depth kind %d", kind);
     if (c->need_low[1].lo < c->own_low[1].lo || c->need_low[1].hi > c->own_low[1].hi)
         return fail(c, MEAO_ERR_INVALID, "interior row band: use meao_render_band_prepare / halo exchange / meao_render_band_finish");
-    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     if (c->flags & MEAO_FLAG_NO_GRAPH) return record_frame(c, depth, kind, ao_out, s, false);
 
     // plan-once / replay: one captured graph per (depth, out, kind); re-captured when they change
@@ -750,21 +754,21 @@ int meao_stage_downsample(MeaoCtx *c, const void *depth, int32_t kind, void *str
 {
     int rc = ensure_ready(c); if (rc) return rc;
     if (!depth) return fail(c, MEAO_ERR_INVALID, "depth is NULL");
-    return record_downsample(c, depth, kind, stream ? (cudaStream_t)stream : c->stream);
+    return record_downsample(c, depth, kind, (cudaStream_t)stream);
 }
 
 int meao_stage_render(MeaoCtx *c, int32_t level, void *stream)
 {
     int rc = ensure_ready(c); if (rc) return rc;
     if (level < 1 || level > 4) return fail(c, MEAO_ERR_INVALID, "render level %d not in 1..4", level);
-    return record_render(c, level, c->last_kind, stream ? (cudaStream_t)stream : c->stream);
+    return record_render(c, level, c->last_kind, (cudaStream_t)stream);
 }
 
 int meao_stage_upsample(MeaoCtx *c, int32_t lo_level, void *ao_out, void *stream)
 {
     int rc = ensure_ready(c); if (rc) return rc;
     if (lo_level < 1 || lo_level > 4) return fail(c, MEAO_ERR_INVALID, "upsample lo level %d not in 1..4", lo_level);
-    return record_upsample(c, lo_level, lo_level == 1 ? ao_out : nullptr, stream ? (cudaStream_t)stream : c->stream);
+    return record_upsample(c, lo_level, lo_level == 1 ? ao_out : nullptr, (cudaStream_t)stream);
 }
 
 int meao_buffer_desc(const MeaoCtx *c, int32_t id, MeaoBufferDesc *out)
@@ -783,6 +787,7 @@ int meao_get_buffer(MeaoCtx *c, int32_t id, void *host_out, size_t host_bytes)
     if (!host_out || buffer_info(c, id, &lvl, &slices, &elem)) return fail(c, MEAO_ERR_INVALID, "bad buffer id %d", id);
     const size_t need = (size_t)c->lw[lvl] * c->lh[lvl] * slices * elem;
     if (host_bytes < need) return fail(c, MEAO_ERR_INVALID, "buffer %d needs %zu bytes, got %zu", id, need, host_bytes);
+    CUDA_TRY(c, cudaDeviceSynchronize());     // debug path: frames may be in flight on any caller stream
     if (slices == 16) {
         const int k = id - 5;
         __half *tmp = nullptr;
@@ -798,6 +803,13 @@ int meao_get_buffer(MeaoCtx *c, int32_t id, void *host_out, size_t host_bytes)
     void *p; size_t pitch;
     buffer_ptr(c, id, &p, &pitch);
     const size_t wb = (size_t)c->lw[lvl] * elem;
+    if (id == MEAO_BUF_AMBIENT_OCCLUSION && c->last_out) {
+        // the last frame wrote the AO texture straight into the caller's buffer; regenerate the debug view
+        // from the (still resident) Combined1 / LowDepth1 / LinearDepth with the same kernel
+        const int64_t before = c->launches;
+        if ((rc = record_upsample(c, 1, nullptr, c->stream))) return rc;
+        c->launches = before;
+    }
     CUDA_TRY(c, cudaMemcpy2DAsync(host_out, wb, p, pitch, wb, c->lh[lvl], cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return MEAO_OK;
@@ -814,6 +826,7 @@ int meao_set_buffer(MeaoCtx *c, int32_t id, const void *host_in, size_t host_byt
     void *p; size_t pitch;
     buffer_ptr(c, id, &p, &pitch);
     const size_t wb = (size_t)c->lw[lvl] * elem;
+    CUDA_TRY(c, cudaDeviceSynchronize());
     CUDA_TRY(c, cudaMemcpy2DAsync(p, pitch, host_in, wb, wb, c->lh[lvl], cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return MEAO_OK;
@@ -910,6 +923,7 @@ int meao_profile_frame(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out
 {
     int rc = ensure_ready(c); if (rc) return rc;
     if (!depth || !ao_out) return fail(c, MEAO_ERR_INVALID, "depth / ao_out is NULL");
+    CUDA_TRY(c, cudaDeviceSynchronize());
     if ((rc = record_frame(c, depth, kind, ao_out, c->stream, true))) return rc;
     const int n = (int)c->last_profile.size();
     for (int i = 0; i < n && i < capacity; i++) {
