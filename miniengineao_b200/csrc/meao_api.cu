@@ -95,9 +95,10 @@ struct MeaoCtx {
 
     int64_t launches = 0;
 
-    // CUDA graph cache (one entry: last (depth, out, kind, stream-independent))
-    cudaGraphExec_t graph_exec = nullptr;
-    const void *graph_depth = nullptr; void *graph_out = nullptr; int graph_kind = -1;
+    // CUDA graph cache: one instantiated graph per (depth, out, kind); dropped whenever the plan changes
+    struct GraphKey { const void *depth; void *out; int kind; bool operator<(const GraphKey &o) const {
+        return depth != o.depth ? depth < o.depth : (out != o.out ? out < o.out : kind < o.kind); } };
+    std::map<GraphKey, cudaGraphExec_t> graphs;
     void *last_out = nullptr;               // where the last final upsample wrote (nullptr: c->result)
     int last_kind = MEAO_DEPTH_RAW_F32;     // ingest kind of the last downsample (selects the atlas padding value)
 
@@ -189,8 +190,8 @@ void build_plan(MeaoCtx *c)
 
 void drop_graph(MeaoCtx *c)
 {
-    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-    c->graph_depth = nullptr; c->graph_out = nullptr; c->graph_kind = -1;
+    for (auto &kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    c->graphs.clear();
 }
 
 void free_buffers(MeaoCtx *c)
@@ -700,9 +701,12 @@ int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void 
     cudaStream_t s = (cudaStream_t)stream;
     if (c->flags & MEAO_FLAG_NO_GRAPH) return record_frame(c, depth, kind, ao_out, s, false);
 
-    // plan-once / replay: one captured graph per (depth, out, kind); re-captured when they change
-    if (!c->graph_exec || c->graph_depth != depth || c->graph_out != ao_out || c->graph_kind != kind) {
-        drop_graph(c);
+    // plan-once / replay: one captured graph per (depth, out, kind), like the reference's command buffer
+    // that is re-recorded only when something changed (AO.cs:334-347)
+    const MeaoCtx::GraphKey key{depth, ao_out, kind};
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+        if (c->graphs.size() >= 64) drop_graph(c);
         cudaGraph_t g = nullptr;
         CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t before = c->launches;
@@ -711,12 +715,14 @@ int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void 
         cudaError_t e = cudaStreamEndCapture(c->stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-        e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+        cudaGraphExec_t ge = nullptr;
+        e = cudaGraphInstantiate(&ge, g, 0);
         cudaGraphDestroy(g);
-        if (e != cudaSuccess) { c->graph_exec = nullptr; return fail(c, MEAO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
-        c->graph_depth = depth; c->graph_out = ao_out; c->graph_kind = kind;
+        if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        it = c->graphs.emplace(key, ge).first;
     }
-    CUDA_TRY(c, cudaGraphLaunch(c->graph_exec, s));
+    c->last_kind = kind; c->last_out = ao_out;
+    CUDA_TRY(c, cudaGraphLaunch(it->second, s));
     c->launches += meao_kernels_per_frame(c);
     return MEAO_OK;
 }

@@ -1,0 +1,50 @@
+"""Generates tests/golden/*.npz from the CPU oracle (oracle/meao_oracle.c).
+
+The reference (HLSL compute + Unity C#) cannot be executed in this image and ships no golden vectors of
+its own, so these fixtures are SELF-GENERATED: they pin the oracle against regressions
+and let the GPU tests compare against committed bytes without running the oracle.  Re-run:
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from miniengineao_b200 import synth  # noqa: E402
+from oracle.oracle import Oracle  # noqa: E402
+
+CASES = {
+    # name: (W, H, lin01 generator, oracle kwargs)
+    "flat_sphere_96": (96, 96, lambda: synth.flat_sphere(96, 96), dict()),
+    "random_83x61_sponza_intensity": (83, 61, lambda: synth.random_depth(83, 61, seed=42), dict(intensity=1.1)),
+    "random_130x70_params": (130, 70, lambda: synth.random_depth(130, 70, seed=7),
+                             dict(intensity=1.2, thickness_modifier=2.0, blur_tolerance=-3.0, upsample_tolerance=-5.0, noise_filter_tolerance=-1.0)),
+    "corridor_160x90": (160, 90, lambda: synth.corridor(160, 90), dict(intensity=1.1)),
+}
+
+
+def main():
+    for name, (W, H, gen, kw) in CASES.items():
+        lin = gen()
+        depth = synth.lin01_to_raw(lin)
+        o = Oracle(W, H, **kw)
+        ao = o.run(depth)
+        data = {"depth": depth, "ao": ao, "params": np.array([kw.get("noise_filter_tolerance", 0.0), kw.get("blur_tolerance", -4.6),
+                                                              kw.get("upsample_tolerance", -12.0), kw.get("thickness_modifier", 1.0),
+                                                              kw.get("intensity", 1.0)], np.float32)}
+        for bid in range(1, 18):
+            b = o.buffer(bid)
+            if bid >= 10:
+                data[f"buf{bid}"] = o.codes(bid)
+            elif bid == 1 or 6 <= bid <= 9:
+                data[f"buf{bid}"] = b.astype(np.float16)
+            else:
+                data[f"buf{bid}"] = b.copy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
+        print(name, W, H, "ao mean", ao.mean())
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,137 @@
+"""CPU tests of the C-ABI library: it loads without a GPU or driver, exports every symbol include/meao.h
+declares, fails LOUDLY when asked to compute without a device, and its host-side planner (constants,
+geometry, band/halo ranges) agrees with the oracle's restatement of AmbientOcclusion.cs."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from miniengineao_b200 import AmbientOcclusion, Camera, MeaoError
+from miniengineao_b200 import _native as N
+from oracle.oracle import Oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "meao.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(meao_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = N.lib()
+    decl = _declared_functions()
+    assert len(decl) >= 35
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/meao.h but not exported"
+        assert name in N.SIGNATURES, f"{name} has no ctypes signature in _native.py"
+    out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (meao_[a-z0-9_]+)", out))
+    assert set(decl) <= exported
+    assert lib.meao_abi_version() == 1
+
+
+def test_library_has_no_driver_link_dependency():
+    out = subprocess.run(["ldd", N.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libcudart" not in out and "libtorch" not in out
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(MeaoError) as e:
+        AmbientOcclusion(Camera(64, 64), device=0)
+    assert e.value.code == N.MEAO_ERR_CUDA and "no CPU fallback" in str(e.value)
+    plan = AmbientOcclusion(Camera(64, 64), device=-1)          # planning-only context
+    with pytest.raises(MeaoError) as e2:
+        plan.render_host(np.zeros((64, 64), np.float32))
+    assert e2.value.code == N.MEAO_ERR_CUDA
+
+
+def test_default_params_match_component():
+    p = N.MeaoParams()
+    N.lib().meao_default_params(C.byref(p))
+    assert (p.noise_filter_tolerance, p.upsample_tolerance, p.thickness_modifier, p.intensity) == (0.0, -12.0, 1.0, 1.0)
+    assert abs(p.blur_tolerance + 4.6) < 1e-6 and p.debug == 0 and p.ambient_only == 1     # AO.cs:20-68
+
+
+@pytest.mark.parametrize("W,H", [(3840, 2160), (1920, 1080), (256, 256), (641, 363)])
+@pytest.mark.parametrize("kw", [dict(), dict(intensity=1.1, thickness_modifier=3.0, blur_tolerance=-2.5, upsample_tolerance=-7.0, noise_filter_tolerance=-4.0)])
+def test_planner_constants_equal_oracle_constants(W, H, kw):
+    ao = AmbientOcclusion(Camera(W, H), device=-1)
+    for py, cs in (("noise_filter_tolerance", "noiseFilterTolerance"), ("blur_tolerance", "blurTolerance"), ("upsample_tolerance", "upsampleTolerance"),
+                   ("thickness_modifier", "thicknessModifier"), ("intensity", "intensity")):
+        if py in kw:
+            setattr(ao, cs, kw[py])
+    o = Oracle(W, H, tan_half_fov_h_=1.0 / Camera(W, H).projection00, **kw)
+    assert np.array_equal(ao.zbuffer_params(), o.zbuffer_params())
+    for k in range(1, 5):
+        a, b = ao.render_constants(k), o.render_constants(k)
+        for key in a:
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), (k, key)
+        a, b = ao.upsample_constants(k), o.upsample_constants(k)
+        for key in a:
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), (k, key)
+
+
+def test_late_update_change_detection():
+    """CheckPropertiesChanged / CheckBaseDimensions semantics (AO.cs:104-113, 338-341)."""
+    ao = AmbientOcclusion(Camera(640, 360), device=-1)
+    assert ao.LateUpdate() is True          # first frame: size set
+    assert ao.LateUpdate() is False
+    ao.intensity = 1.5
+    assert ao.LateUpdate() is True
+    ao.intensity = 1.5
+    assert ao.LateUpdate() is False
+    ao.ambientOnly = False                  # not part of CheckPropertiesChanged in the reference either
+    assert ao.LateUpdate() is False
+    ao.camera.pixelWidth = 800
+    assert ao.LateUpdate() is True
+    assert ao.rebuild_count == 3
+
+
+def test_algorithmic_bytes_match_survey_table():
+    for (W, H), mb in (((256, 256), 1.040), ((1920, 1080), 32.908), ((3840, 2160), 131.614), ((7680, 4320), 526.439)):
+        ao = AmbientOcclusion(Camera(W, H), device=-1)
+        assert abs(ao.algorithmic_bytes(0) / 1e6 - mb) < 0.002
+        assert ao.algorithmic_bytes(0) == sum(ao.algorithmic_bytes(s) for s in (1, 2, 3, 4))
+
+
+def test_band_planning_halo_symmetry_and_limits():
+    W, H = 7680, 4320
+    bands = 8
+    blocks = (H + 15) // 16
+    cuts = [min(H, 16 * ((blocks * i) // bands)) for i in range(bands)] + [H]
+    ctxs = []
+    for i in range(bands):
+        a = AmbientOcclusion(Camera(W, H), device=-1)
+        a.set_row_band(cuts[i], cuts[i + 1], cuts[i - 1] if i > 0 else -1, cuts[i + 2] if i + 2 <= bands else -1)
+        ctxs.append(a)
+    for i in range(bands):
+        rows = ctxs[i].band_rows()
+        assert rows["produce"][0] == (cuts[i], cuts[i + 1])
+        for k in range(1, 5):
+            lo, hi = rows["need_low"][k]
+            olo, ohi = rows["own_low"][k]
+            assert lo <= olo and hi >= ohi
+            assert olo == cuts[i] >> k
+        for side, j in ((0, i - 1), (1, i + 1)):
+            if 0 <= j < bands:
+                assert ctxs[i].halo_rows(side, True) == ctxs[j].halo_rows(1 - side, False)      # what i sends == what j expects
+                assert ctxs[i].halo_bytes(side) == ctxs[j].halo_recv_bytes(1 - side) > 0
+            else:
+                assert ctxs[i].halo_bytes(side) == 0
+    # per-level halo is about 0.7 MB per direction at 8K, far below a raw-depth halo (346 rows)
+    assert ctxs[3].halo_bytes(0) < 1.2e6
+    thin = AmbientOcclusion(Camera(1920, 1088), device=-1)
+    with pytest.raises(MeaoError) as e:
+        thin.set_row_band(272, 544, 0, 816)
+    assert e.value.code == N.MEAO_ERR_UNSUPPORTED
+    with pytest.raises(MeaoError):
+        thin.set_row_band(100, 544, 0, 816)         # not 16-row aligned
