@@ -201,6 +201,10 @@ int64_t meao_algorithmic_bytes(const MeaoCtx *ctx, int32_t stage);
 int meao_profile_frame(MeaoCtx *ctx, const void *depth_dev, int32_t depth_kind, void *ao_out_dev,
                        float *ms_out, const char **names_out, int32_t capacity);
 
+/* Device self test: compares the guarded fast division / reciprocal the kernels use (MUFU.RCP + FMA
+ * refinement, csrc/common.cuh) with the IEEE operators on n random operand pairs; *mismatches must be 0. */
+int meao_selftest_div(MeaoCtx *ctx, uint64_t n, uint32_t seed, uint64_t *mismatches);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

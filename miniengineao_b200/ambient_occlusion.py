@@ -275,6 +275,13 @@ class AmbientOcclusion:
         self.LateUpdate()
         return self._check(self._lib.meao_algorithmic_bytes(self._ctx, stage))
 
+    def selftest_div(self, n: int = 1 << 28, seed: int = 1) -> int:
+        """Mismatches between the kernels' guarded fast division / reciprocal and the IEEE operators (must be 0)."""
+        self.LateUpdate()
+        m = C.c_uint64(0)
+        self._check(self._lib.meao_selftest_div(self._ctx, n, seed, C.byref(m)))
+        return int(m.value)
+
     def profile_frame(self, depth, out, *, linear: bool = False) -> list[tuple[str, float]]:
         self.LateUpdate()
         n = self.kernels_per_frame

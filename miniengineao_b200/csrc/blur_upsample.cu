@@ -30,6 +30,8 @@ namespace {
 constexpr int kHW = 64, kHH = 32;               // hi-res outputs per CTA
 constexpr int kRawW = 38, kRawH = 22;           // low-res footprint actually used
 constexpr int kRawP = 40;                       // pitch of the raw arrays
+constexpr int kLoDP = 42;                       // pitch of the lo_depth array: 4 rows apart = 168 words = 8 banks, so the four
+                                                // row groups of a warp read distinct banks in the upsample phase
 constexpr int kBoxDP = kUpsDepthBoxW;           // 40: depth TMA box width  (box column = raw column + kBoxDOff)
 constexpr int kBoxAP = kUpsAoBoxW;              // 64: AO TMA box width     (box column = raw column + kBoxAOff)
 // MEASURED on B200: cp.async.bulk.tensor (tiled, no swizzle) raises "illegal instruction" unless the
@@ -44,7 +46,7 @@ static_assert(kRawH == kUpsDepthBoxH && kRawH == kUpsAoBoxH, "TMA box mismatch")
 struct __align__(128) Smem {
     alignas(128) float box_depth[kRawH * kBoxDP];   // TMA destination: low-res depth box (LoResDB)
     alignas(128) uint8_t box_ao[kRawH * kBoxAP];    // TMA destination: low-res AO codes box (LoResAO1)
-    alignas(16) float lo_depth[kRawH * kRawP];      // raw low-res depth, column 0 = virtual column lx0
+    alignas(16) float lo_depth[kRawH * kLoDP];      // raw low-res depth, column 0 = virtual column lx0
     alignas(16) float inv_depth[kRawH * kRawP];     // DepthCache, UPS:67-71
     alignas(16) float ao[kRawH * kRawP];            // AOCache1 as loaded, UPS:62-65
     alignas(16) float hblur[kRawH * kBlurP];        // AOCache2, UPS:127-129
@@ -70,19 +72,35 @@ __device__ __forceinline__ bool compare_deltas(float d1, float d2, float l1, flo
     return __fmul_rn(temp, temp) > __fmul_rn(__fmul_rn(l1, l2), kblur);
 }
 
-// Upsample.compute:177-183 with the swizzled argument order of :229-232
+// Upsample.compute:177-183 with the swizzled argument order of :229-232.
+// FAST: the five divisions use div_fast (common.cuh) and `ok` collects the validity guard of the whole
+// group; when it ends up false the caller recomputes with FAST = false (plain IEEE operators).
+template <bool FAST, bool BLEND>
 __device__ __forceinline__ float bilateral(float hi_depth, float hi_ao,
                                            float ld0, float ld1, float ld2, float ld3,
                                            float la0, float la1, float la2, float la3,
-                                           float tol, float nfs)
+                                           float tol, float nfs, bool &ok)
 {
-    const float w0 = 9.0f / __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld0)), tol);
-    const float w1 = 3.0f / __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld1)), tol);
-    const float w2 = 1.0f / __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld2)), tol);
-    const float w3 = 3.0f / __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld3)), tol);
+    const float b0 = __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld0)), tol);
+    const float b1 = __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld1)), tol);
+    const float b2 = __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld2)), tol);
+    const float b3 = __fadd_rn(fabsf(__fadd_rn(hi_depth, -ld3)), tol);
+    float w0, w1, w2, w3;
+    if (FAST) {
+        // every b_i >= tol >= 2^-60 (host-checked); their sum < 2^60 bounds them above and catches inf / NaN
+        ok = ok & (__fadd_rn(__fadd_rn(b0, b1), __fadd_rn(b2, b3)) < 1152921504606846976.0f);
+        w0 = div_fast(9.0f, b0); w1 = div_fast(3.0f, b1); w2 = div_fast(1.0f, b2); w3 = div_fast(3.0f, b3);
+    } else {
+        w0 = 9.0f / b0; w1 = 3.0f / b1; w2 = 1.0f / b2; w3 = 3.0f / b3;
+    }
     const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(w0, w1), w2), w3), nfs);
     const float wsum = __fadd_rn(fmaf(la3, w3, fmaf(la2, w2, fmaf(la1, w1, __fmul_rn(la0, w0)))), nfs);
-    return __fmul_rn(hi_ao, wsum) / total;
+    const float num = BLEND ? __fmul_rn(hi_ao, wsum) : wsum;      // HiSSAOs = 1 without blend (UPS:223): 1 * x == x
+    if (FAST) {
+        ok = ok & in_safe_range(total) & ((num == 0.0f) | in_safe_range(num));
+        return div_fast(num, total);
+    }
+    return num / total;
 }
 
 template <bool BLEND, bool HI_HALF>
@@ -110,8 +128,8 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
         for (int idx = tid; idx < kRawH * kRawP; idx += kThreads) {
             const int r = idx / kRawP, c = idx - r * kRawP;
             const float d = (c + kBoxDOff < kBoxDP) ? sm.box_depth[r * kBoxDP + c + kBoxDOff] : 1.0f;   // column 39 is never consumed
-            sm.lo_depth[r * kRawP + c] = d;
-            sm.inv_depth[r * kRawP + c] = 1.0f / d;                                          // UPS:67
+            sm.lo_depth[r * kLoDP + c] = d;
+            sm.inv_depth[r * kRawP + c] = rcp_ieee(d);                                       // UPS:67
             sm.ao[r * kRawP + c] = unorm8_load(sm.box_ao[r * kBoxAP + c + kBoxAOff]);
         }
     } else {
@@ -120,8 +138,8 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
             const int r = idx / kRawP, c = idx - r * kRawP;
             const int sx = iclamp(lx0 + c, 0, a.low - 1), sy = iclamp(ly0 + r, 0, a.loh - 1);
             const float d = __ldg(a.lo_depth + (size_t)sy * a.lo_dpitch + sx);
-            sm.lo_depth[r * kRawP + c] = d;
-            sm.inv_depth[r * kRawP + c] = 1.0f / d;
+            sm.lo_depth[r * kLoDP + c] = d;
+            sm.inv_depth[r * kRawP + c] = rcp_ieee(d);
             sm.ao[r * kRawP + c] = unorm8_load(__ldg(a.lo_ao + (size_t)sy * a.lo_apitch + sx));
         }
     }
@@ -175,7 +193,9 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
     __syncthreads();
 
     // ---- bilateral upsample, UPS:213-232: thread -> 8 consecutive hi-res pixels of one row ----------
-    const int j = tid & 7, hy = tid >> 3;
+    // a warp takes rows w, w+8, w+16, w+24 of the tile: the row parity (which selects the operand order of
+    // UPS:229-232) is then warp-uniform and the parity branch below never diverges
+    const int j = tid & 7, hy = ((tid >> 3) & 3) * 8 + (tid >> 5);
     const int py = hy0 + hy, px0 = hx0 + 8 * j;
     if (py < a.row0 || py >= a.row1 || px0 >= a.hiw) return;
 
@@ -185,7 +205,7 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
         const float *vb = &sm.vblur[(rY - 1 + rr) * kBlurP + 4 * j];
-        const float *ld = &sm.lo_depth[(rY - 1 + rr + 2) * kRawP + 4 * j + 2];
+        const float *ld = &sm.lo_depth[(rY - 1 + rr + 2) * kLoDP + 4 * j + 2];
         const float4 v4 = *reinterpret_cast<const float4 *>(vb);
         const float2 v2 = *reinterpret_cast<const float2 *>(vb + 4);
         bl_ao[rr][0] = v4.x; bl_ao[rr][1] = v4.y; bl_ao[rr][2] = v4.z; bl_ao[rr][3] = v4.w; bl_ao[rr][4] = v2.x; bl_ao[rr][5] = v2.y;
@@ -236,22 +256,31 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
     const float tol = a.upsample_tolerance, nfs = a.noise_filter_strength;
     const bool y_odd = (py & 1) != 0;     // py = 2Y-1 (odd) or 2Y (even)
     uint32_t code[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-        // X - 1 -> local index m, X -> m + 1, with m = (e + 1) >> 1 relative to blurred column 4j
-        const int m = (e + 1) >> 1;
-        const float tl_d = lo_d[0][m], tr_d = lo_d[0][m + 1], bl_d = lo_d[1][m], br_d = lo_d[1][m + 1];
-        const float tl_a = bl_ao[0][m], tr_a = bl_ao[0][m + 1], bl_a = bl_ao[1][m], br_a = bl_ao[1][m + 1];
-        float r;
-        if ((e & 1) != 0) {            // px odd = 2X-1
-            if (!y_odd) r = bilateral(hd[e], ha[e], bl_d, br_d, tr_d, tl_d, bl_a, br_a, tr_a, tl_a, tol, nfs);   // UPS:229 (-1, 0) .xyzw
-            else        r = bilateral(hd[e], ha[e], tl_d, bl_d, br_d, tr_d, tl_a, bl_a, br_a, tr_a, tol, nfs);   // UPS:232 (-1,-1) .wxyz
-        } else {                       // px even = 2X
-            if (!y_odd) r = bilateral(hd[e], ha[e], br_d, tr_d, tl_d, bl_d, br_a, tr_a, tl_a, bl_a, tol, nfs);   // UPS:230 ( 0, 0) .yzwx
-            else        r = bilateral(hd[e], ha[e], tr_d, tl_d, bl_d, br_d, tr_a, tl_a, bl_a, br_a, tol, nfs);   // UPS:231 ( 0,-1) .zwxy
-        }
-        code[e] = unorm8_code(r);
+    // X - 1 -> local index m, X -> m + 1, with m = (e + 1) >> 1 relative to blurred column 4j
+#define MEAO_UPS_PIXELS(FAST, YODD, OK)                                                                                         \
+    _Pragma("unroll") for (int e = 0; e < 8; e++) {                                                                             \
+        const int m = (e + 1) >> 1;                                                                                             \
+        const float tl_d = lo_d[0][m], tr_d = lo_d[0][m + 1], bl_d = lo_d[1][m], br_d = lo_d[1][m + 1];                         \
+        const float tl_a = bl_ao[0][m], tr_a = bl_ao[0][m + 1], bl_a = bl_ao[1][m], br_a = bl_ao[1][m + 1];                     \
+        float r;                                                                                                                \
+        if ((e & 1) != 0) { /* px odd = 2X-1 */                                                                                 \
+            if (!(YODD)) r = bilateral<FAST, BLEND>(hd[e], ha[e], bl_d, br_d, tr_d, tl_d, bl_a, br_a, tr_a, tl_a, tol, nfs, OK); /* UPS:229 (-1, 0) .xyzw */ \
+            else         r = bilateral<FAST, BLEND>(hd[e], ha[e], tl_d, bl_d, br_d, tr_d, tl_a, bl_a, br_a, tr_a, tol, nfs, OK); /* UPS:232 (-1,-1) .wxyz */ \
+        } else {            /* px even = 2X */                                                                                  \
+            if (!(YODD)) r = bilateral<FAST, BLEND>(hd[e], ha[e], br_d, tr_d, tl_d, bl_d, br_a, tr_a, tl_a, bl_a, tol, nfs, OK); /* UPS:230 ( 0, 0) .yzwx */ \
+            else         r = bilateral<FAST, BLEND>(hd[e], ha[e], tr_d, tl_d, bl_d, br_d, tr_a, tl_a, bl_a, br_a, tol, nfs, OK); /* UPS:231 ( 0,-1) .zwxy */ \
+        }                                                                                                                       \
+        code[e] = unorm8_code(r);                                                                                               \
     }
+    bool ok = a.fast_div_ok != 0;
+    if (ok) {
+        if (y_odd) { MEAO_UPS_PIXELS(true, true, ok) } else { MEAO_UPS_PIXELS(true, false, ok) }
+    }
+    if (!ok) {      // rare: inf / NaN / zero / denormal operands somewhere in this thread's 8 pixels -> plain IEEE operators
+        bool unused = true;
+        MEAO_UPS_PIXELS(false, y_odd, unused)
+    }
+#undef MEAO_UPS_PIXELS
 
     uint8_t *dst = a.out + (size_t)(py - a.out_row_origin) * a.out_pitch + px0;
     if (full && a.out_vec_ok) {

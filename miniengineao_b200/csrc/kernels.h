@@ -66,6 +66,7 @@ struct UpsampleArgs {
     int out_vec_ok;         // out is 8B aligned and out_pitch % 8 == 0
     int hiw, hih;
     float noise_filter_strength, step_size, blur_tolerance, upsample_tolerance;
+    int fast_div_ok;        // upsample_tolerance and noise_filter_strength are positive normals in [2^-60, 2^60)
     int row0, row1;         // output rows (hi level) to produce
 };
 cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensorMap &lo_ao_map, bool use_tma,
@@ -76,6 +77,9 @@ constexpr int kUpsAoBoxW = 64, kUpsAoBoxH = 22;
 // ---- debug: synthesise a TiledDepth<k> view (reference layout [16][sh][sw], f16 bits) ----------
 cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int sw, int sh, float pad,
                                __half *out, cudaStream_t s);
+
+// ---- self test: div_fast / rcp_fast vs the IEEE operators on n random in-range operand pairs ------
+cudaError_t launch_selftest_div(uint64_t n, uint32_t seed, unsigned long long *mismatch_dev, cudaStream_t s);
 
 // ---- halo pack / unpack: rows [r0, r1) of a pitched buffer <-> contiguous staging --------------
 // (plain cudaMemcpy2DAsync is used; no kernel)

@@ -59,6 +59,8 @@ struct MeaoCtx {
     uint32_t flags = 0;
     std::string error;
     cudaStream_t stream = nullptr;
+    cudaStream_t branch[3] = {nullptr, nullptr, nullptr};   // forked capture streams: the graph runs independent levels side by side
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     PFN_encodeTiled encode = nullptr;
 
     MeaoParams params;
@@ -402,9 +404,42 @@ int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
     a.step_size = c->plan.step_size[lo];
     a.blur_tolerance = c->plan.blur_tolerance[lo];
     a.upsample_tolerance = c->plan.upsample_tolerance[lo];
+    {
+        auto safe = [](float x) { return x >= 8.673617379884035e-19f && x < 1152921504606846976.0f; };
+        a.fast_div_ok = safe(a.upsample_tolerance) && safe(a.noise_filter_strength);
+    }
     a.row0 = c->need_c[hi].lo; a.row1 = c->need_c[hi].hi;
     CUDA_TRY(c, launch_blur_upsample(c->map_low_ups[lo], c->map_ao_ups[lo], c->tma_ok, a, s));
     c->launches++;
+    return 0;
+}
+
+// The same nine launches as record_frame, recorded as a DAG on forked streams (for graph capture): the four
+// render levels are independent, the coarse upsample chain 4->3->2 only needs Occlusion2..4,
+// and only the last two upsamples wait for the big level-1 render.
+int record_frame_dag(MeaoCtx *c, const void *depth, int kind, void *ao_out, cudaStream_t s)
+{
+    int rc;
+    cudaStream_t b1 = c->branch[0], b2 = c->branch[1], b3 = c->branch[2];
+    if ((rc = record_downsample(c, depth, kind, s))) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->ev[0], s));
+    CUDA_TRY(c, cudaStreamWaitEvent(b1, c->ev[0], 0));
+    CUDA_TRY(c, cudaStreamWaitEvent(b2, c->ev[0], 0));
+    CUDA_TRY(c, cudaStreamWaitEvent(b3, c->ev[0], 0));
+    if ((rc = record_render(c, 1, kind, s))) return rc;
+    if ((rc = record_render(c, 2, kind, b1))) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->ev[1], b1));
+    if ((rc = record_render(c, 3, kind, b2))) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->ev[2], b2));
+    if ((rc = record_render(c, 4, kind, b3))) return rc;
+    CUDA_TRY(c, cudaStreamWaitEvent(b3, c->ev[2], 0));
+    if ((rc = record_upsample(c, 4, nullptr, b3))) return rc;
+    CUDA_TRY(c, cudaStreamWaitEvent(b3, c->ev[1], 0));
+    if ((rc = record_upsample(c, 3, nullptr, b3))) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->ev[3], b3));
+    CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev[3], 0));
+    if ((rc = record_upsample(c, 2, nullptr, s))) return rc;
+    if ((rc = record_upsample(c, 1, ao_out, s))) return rc;
     return 0;
 }
 
@@ -515,6 +550,8 @@ int meao_create(const MeaoDeviceCfg *cfg, MeaoCtx **out)
     meao_default_params(&c->params);
     c->camera = MeaoCamera{0.3f, 1000.0f, 1.0f, 1};
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&c->branch[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) { delete c; return fail(nullptr, MEAO_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -539,6 +576,8 @@ void meao_destroy(MeaoCtx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     free_buffers(c);
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (auto b : c->branch) if (b) cudaStreamDestroy(b);
+    for (auto e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -710,7 +749,7 @@ int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void 
         cudaGraph_t g = nullptr;
         CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t before = c->launches;
-        rc = record_frame(c, depth, kind, ao_out, c->stream, false);
+        rc = record_frame_dag(c, depth, kind, ao_out, c->stream);
         c->launches = before;
         cudaError_t e = cudaStreamEndCapture(c->stream, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
@@ -923,6 +962,23 @@ int64_t meao_algorithmic_bytes(const MeaoCtx *c, int32_t stage)
         case 5: return ups_final;
         default: return MEAO_ERR_INVALID;
     }
+}
+
+int meao_selftest_div(MeaoCtx *c, uint64_t n, uint32_t seed, uint64_t *mismatches)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!mismatches) return fail(c, MEAO_ERR_INVALID, "mismatches is NULL");
+    unsigned long long *d = nullptr;
+    CUDA_TRY(c, cudaMalloc(&d, sizeof *d));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof *d, c->stream);
+    if (e == cudaSuccess) e = launch_selftest_div(n, seed, d, c->stream);
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
+    *mismatches = h;
+    return MEAO_OK;
 }
 
 int meao_profile_frame(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, float *ms_out, const char **names_out, int32_t capacity)

@@ -24,7 +24,7 @@ template <bool RAW, bool REVERSED>
 __device__ __forceinline__ float linearize(float depth, float zbx, float zby)
 {
     if (!RAW) return depth;
-    float dist = 1.0f / fmaf(zbx, depth, zby);          // DS1:40 (mad + IEEE reciprocal)
+    float dist = rcp_ieee(fmaf(zbx, depth, zby));       // DS1:40 (mad + IEEE reciprocal)
     if (REVERSED) { if (depth == 0.0f) dist = 1e5f; }   // DS1:41-42
     else          { if (depth == 1.0f) dist = 1e5f; }   // DS1:43-44
     return dist;

@@ -153,7 +153,7 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
         if (oy < a.row0 || oy >= a.row1 || ox >= a.lw) continue;
         const float *c = tile + (row + kAp) * kSW + (px + kAp);
         const float2 ctr = *reinterpret_cast<const float2 *>(c);
-        const float inv0 = 1.0f / ctr.x, inv1 = 1.0f / ctr.y;                // REN:140
+        const float inv0 = rcp_ieee(ctr.x), inv1 = rcp_ieee(ctr.y);              // REN:140
         float ao0 = 0.0f, ao1 = 0.0f;                                        // REN:142
         // REN:162-168 -- the 36-sample checker pattern, in call order
         axial2<2>(c, inv0, inv1, a.inv_thickness[0], a.neg_front[0], a.weight[0], rf, ao0, ao1);

@@ -329,3 +329,12 @@ def test_too_thin_band_is_refused(torch_cuda):
     with pytest.raises(MeaoError) as e:
         a.set_row_band(272, 544, 0, 816)
     assert e.value.code == -3
+
+
+def test_fast_division_is_ieee_exact(torch_cuda):
+    """The kernels replace nvcc's `a / b` expansion by its own fast path (MUFU.RCP + FMA refinement) under a
+    stricter operand guard (csrc/common.cuh).  Brute force: 2^30 random in-range operand pairs, incl. the
+    numerators 1, 3, 9 and quotients near 1, must give bit-identical results to the IEEE operators."""
+    from miniengineao_b200 import AmbientOcclusion, Camera
+    a = AmbientOcclusion(Camera(64, 64), device=0)
+    assert a.selftest_div(1 << 30, seed=12345) == 0
