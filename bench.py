@@ -159,8 +159,14 @@ def run_ours(args) -> None:
     W, H = WORKLOADS[args.workload]
     K, Wm = args.steps, max(args.warmup, 3)
     NBUF = 8
-    ao = AmbientOcclusion(Camera(W, H), device=local)
-    ao.intensity = INTENSITY
+    S = max(1, args.streams)
+    aos = []
+    for _ in range(S):
+        a_ = AmbientOcclusion(Camera(W, H), device=local)
+        a_.intensity = INTENSITY
+        aos.append(a_)
+    ao = aos[0]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     frames_host = [make_depth(W, H, f + 64 * rank) for f in range(2)]
     # 8 distinct device frames (2 generated + shifted copies: content differs, cost of generation bounded)
     depths = []
@@ -175,28 +181,40 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -----------------------------------------------------------------
-    for i in range(max(Wm, NBUF)):          # warm-up also captures the 8 graphs
-        ao.render(depths[i % NBUF], outs[i % NBUF])
+    def submit(i):
+        # frame i goes to context / stream i % S: independent frames overlap on the device (throughput mode)
+        aos[i % S].render(depths[i % NBUF], outs[i % NBUF], stream=streams[i % S])
+
+    torch.cuda.synchronize()
+    for i in range(max(Wm, NBUF * S)):      # warm-up also captures the graphs
+        submit(i)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    l0 = ao.launch_count
+    l0 = sum(a_.launch_count for a_ in aos)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record()
+    main = torch.cuda.current_stream(dev)
+    e0.record(main)
+    for st in streams:
+        st.wait_event(e0)
     for i in range(K):
-        ao.render(depths[i % NBUF], outs[i % NBUF])
-    e1.record()
+        submit(i)
+    for st in streams:
+        ev = torch.cuda.Event()
+        ev.record(st)
+        main.wait_event(ev)
+    e1.record(main)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ao.launch_count - l0
+    launches = sum(a_.launch_count for a_ in aos) - l0
     # keep the load up a little longer so the 100 ms clock sampler sees it
     t_end = time.time() + 0.6
     while time.time() < t_end:
         for i in range(64):
-            ao.render(depths[i % NBUF], outs[i % NBUF])
+            submit(i)
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -228,6 +246,33 @@ def run_ours(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = W * H * Ke * world / float(t.item()) / 1e6
     e2e_check = int(ho.astype(np.uint64).sum())
+
+    # ---- row-tiled single 8K frame with halo exchange (BASELINE.json configs[3]), only when N > 1 --------------
+    rowtile = None
+    if world > 1 and not args.no_rowtile:
+        from miniengineao_b200 import rowtile as RT, synth
+        RW, RH = WORKLOADS["8k"]
+        rt = RT.RowTiledAO(Camera(RW, RH), rank, world, local, intensity=INTENSITY)
+        band = torch.from_numpy(synth.lin01_to_raw(synth.corridor(RW, RH, row0=rt.row0, row1=rt.row1))).to(dev)
+        oband = torch.empty((rt.rows, RW), dtype=torch.uint8, device=dev)
+        Kr = max(3, min(K, 100))
+        for _ in range(5):
+            rt.step(band, oband)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(Kr):
+            rt.step(band, oband)
+        r1.record()
+        barrier()
+        tr = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        chk = torch.tensor([float(oband.sum(dtype=torch.float64).item())], dtype=torch.float64, device=dev)
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+        rowtile = {"workload": f"{RW}x{RH} single frame, {world} row bands, per-level LowDepth halo exchange (NCCL P2P)",
+                   "value": round(RW * RH * Kr / (float(tr.item()) * 1e-3) / 1e6, 1), "unit": "Mpixels/s", "steps": Kr,
+                   "ms_per_step": round(float(tr.item()) / Kr, 5), "scaling": "strong",
+                   "halo_bytes_sent_per_step_rank0": int(rt.ao.halo_bytes(0) + rt.ao.halo_bytes(1)), "ao_checksum": int(chk.item())}
 
     # ---- per-kernel device times (events around every kernel), rank 0 ------------------------------------
     roofline, kernels = None, None
@@ -278,9 +323,10 @@ def run_ours(args) -> None:
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{W}x{H} synthetic Sponza-like corridor depth, full multi-scale pipe, component defaults, intensity {INTENSITY}",
                            "per_gpu": "one frame per step on every rank (frames are independent; no data-path collective)",
+                           "streams": f"{S} contexts on {S} CUDA streams, frames alternate (throughput mode; --streams 1 = strictly serial frames)",
                            "l2": f"inputs rotate over {NBUF} distinct depth frames ({NBUF * W * H * 4 / 1e6:.0f} MB > 126 MB L2); intermediates stay L2-resident by design"},
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": W * H * 4, "d2h_bytes_per_step": W * H, "steps": Ke},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "rowtile": rowtile}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -294,6 +340,8 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-rowtile", action="store_true", help="skip the row-tiled 8K measurement (N > 1 only)")
+    ap.add_argument("--streams", type=int, default=2, help="contexts/streams that frames alternate over (1 = serial frames)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -47,7 +47,7 @@ struct RenderArgs {
     int row0, row1;         // output rows (level k) to produce
 };
 cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const RenderArgs &a, cudaStream_t s);
-constexpr int kRenderBoxW = 96, kRenderBoxH = 64;     // TMA box of the render kernel (f32 elements)
+constexpr int kRenderBoxW = 96, kRenderBoxH = 48;     // TMA box of the render kernel (f32 elements)
 
 // ---- stage 3: blur_upsample = Upsample.compute main / main_blendout, one level ----------------
 struct UpsampleArgs {

@@ -5,7 +5,7 @@
 //
 // Design (not a port): the reference deinterleaves depth into 16 slices so that its sparse taps
 // become unit-stride texture fetches.  Here the level-k depth stays in NATURAL layout: one CTA
-// stages a (64+32) x (32+32) f32 tile of LowDepth<k> in shared memory with a single TMA box load,
+// stages a (64+32) x (16+32) f32 tile of LowDepth<k> in shared memory with a single TMA box load,
 // rounds it to f16 in place (the reference samples an RHalf atlas), and every thread then reads
 // its 36 taps at stride 4 texels -- which, across a warp of consecutive pixels, is unit-stride and
 // bank-conflict free.  A thread owns two horizontally adjacent pixels so each tap is one LDS.64.
@@ -25,11 +25,13 @@ namespace meao {
 
 namespace {
 
-constexpr int kTW = 64, kTH = 32;           // outputs per CTA
+constexpr int kTW = 64, kTH = 16;           // outputs per CTA (small tiles: 2040 CTAs at 4K L1 keep the last wave short)
 constexpr int kAp = 16;                     // apron: 4 slice texels x stride 4
 constexpr int kSW = kTW + 2 * kAp;          // 96  == kRenderBoxW
-constexpr int kSH = kTH + 2 * kAp;          // 64  == kRenderBoxH
-constexpr int kThreads = 256;
+constexpr int kSH = kTH + 2 * kAp;          // 48  == kRenderBoxH
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+static_assert((kSW * kSH / 4) % kThreads == 0, "tile must split evenly over the threads");
 static_assert(kSW == kRenderBoxW && kSH == kRenderBoxH, "TMA box mismatch");
 
 // Render.compute:60-75 for one sample pair; S1/S2 are the two mirrored taps.
@@ -95,7 +97,7 @@ __device__ __forceinline__ void lshape2(const float *c, float inv0, float inv1, 
     ao1 = fmaf(w, __fmul_rn(0.25f, t1), ao1);
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 8)
 render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a, const int use_tma)
 {
 #ifdef MEAO_DEVICE_OK
@@ -142,13 +144,13 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
     }
     __syncthreads();
 
-    // ---- sampling: thread -> pixels (2*lane, 2*lane+1) of rows wy, wy+8, wy+16, wy+24 ------------
+    // ---- sampling: thread -> pixels (2*lane, 2*lane+1) of rows wy, wy+4, wy+8, wy+12 --------------
     const int lane = tid & 31, wy = tid >> 5;
     const int px = 2 * lane;
     const float rf = a.reject_fadeoff;
 #pragma unroll 1
-    for (int i = 0; i < 4; i++) {
-        const int row = wy + 8 * i;
+    for (int i = 0; i < kTH / kWarps; i++) {
+        const int row = wy + kWarps * i;
         const int oy = Y0 + row, ox = X0 + px;
         if (oy < a.row0 || oy >= a.row1 || ox >= a.lw) continue;
         const float *c = tile + (row + kAp) * kSW + (px + kAp);
