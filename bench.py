@@ -269,10 +269,22 @@ def run_ours(args) -> None:
         dist.all_reduce(tr, op=dist.ReduceOp.MAX)
         chk = torch.tensor([float(oband.sum(dtype=torch.float64).item())], dtype=torch.float64, device=dev)
         dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+        # correctness of the distributed path: the same random frame through ONE full-frame context on this GPU
+        full = synth.lin01_to_raw(synth.random_depth(RW, RH, seed=2024))
+        fd = torch.from_numpy(full).to(dev)
+        whole = AmbientOcclusion(Camera(RW, RH), device=local)
+        whole.intensity = INTENSITY
+        ref_band = whole.render(fd)[rt.row0:rt.row1].clone()
+        rt.step(fd[rt.row0:rt.row1].contiguous(), oband)
+        torch.cuda.synchronize()
+        same = torch.tensor([1.0 if torch.equal(ref_band, oband) else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        del whole, fd, ref_band
         rowtile = {"workload": f"{RW}x{RH} single frame, {world} row bands, per-level LowDepth halo exchange (NCCL P2P)",
                    "value": round(RW * RH * Kr / (float(tr.item()) * 1e-3) / 1e6, 1), "unit": "Mpixels/s", "steps": Kr,
                    "ms_per_step": round(float(tr.item()) / Kr, 5), "scaling": "strong",
-                   "halo_bytes_sent_per_step_rank0": int(rt.ao.halo_bytes(0) + rt.ao.halo_bytes(1)), "ao_checksum": int(chk.item())}
+                   "halo_bytes_sent_per_step_rank0": int(rt.ao.halo_bytes(0) + rt.ao.halo_bytes(1)), "ao_checksum": int(chk.item()),
+                   "bands_match_single_gpu_frame": bool(same.item() == 1.0)}
 
     # ---- per-kernel device times (events around every kernel), rank 0 ------------------------------------
     roofline, kernels = None, None
@@ -341,7 +353,7 @@ def main() -> None:
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rowtile", action="store_true", help="skip the row-tiled 8K measurement (N > 1 only)")
-    ap.add_argument("--streams", type=int, default=2, help="contexts/streams that frames alternate over (1 = serial frames)")
+    ap.add_argument("--streams", type=int, default=3, help="contexts/streams that frames alternate over (1 = serial frames)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

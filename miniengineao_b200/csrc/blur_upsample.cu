@@ -103,6 +103,51 @@ __device__ __forceinline__ float bilateral(float hi_depth, float hi_ao,
     return num / total;
 }
 
+// ---- packed-f32x2 fast path -------------------------------------------------------------------
+// Blackwell's FFMA2 / FADD2 / FMUL2 (PTX fma.rn.f32x2 ...) do two IEEE fp32 operations per lane and per
+// issue slot.  The kernel is issue-bound, so the fast path evaluates TWO pixels of equal x parity
+// (e, e+2: same operand order) with packed arithmetic.  Every lane of every packed instruction performs
+// exactly the scalar operation of bilateral<true>, so the result is bit-identical; nb_i = -(|hi-lo_i| + tol)
+// is formed directly in negated form (a sign flip is exact) because packed ops have no negate modifier.
+__device__ __forceinline__ float2 div2_fast_neg(float2 num, float2 nden)      // num / (-nden), lane-wise div_fast
+{
+    float2 y = make_float2(rcp_approx(-nden.x), rcp_approx(-nden.y));
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2 e = __ffma2_rn(nden, y, one);
+    y = __ffma2_rn(y, e, y);
+    const float2 q = __fmul2_rn(num, y);
+    const float2 r = __ffma2_rn(nden, q, num);
+    return __ffma2_rn(y, r, q);
+}
+
+template <bool BLEND>
+__device__ __forceinline__ float2 bilateral2(float2 hd, float2 ha,
+                                             float2 ld0, float2 ld1, float2 ld2, float2 ld3,
+                                             float2 la0, float2 la1, float2 la2, float2 la3,
+                                             float tol, float nfs, bool &ok)
+{
+    const float2 m1 = make_float2(-1.0f, -1.0f);
+    const float2 t0 = __ffma2_rn(ld0, m1, hd), t1 = __ffma2_rn(ld1, m1, hd);          // hd - ld_i (one rounding, == FADD)
+    const float2 t2 = __ffma2_rn(ld2, m1, hd), t3 = __ffma2_rn(ld3, m1, hd);
+    const float2 nb0 = make_float2(__fadd_rn(-fabsf(t0.x), -tol), __fadd_rn(-fabsf(t0.y), -tol));
+    const float2 nb1 = make_float2(__fadd_rn(-fabsf(t1.x), -tol), __fadd_rn(-fabsf(t1.y), -tol));
+    const float2 nb2 = make_float2(__fadd_rn(-fabsf(t2.x), -tol), __fadd_rn(-fabsf(t2.y), -tol));
+    const float2 nb3 = make_float2(__fadd_rn(-fabsf(t3.x), -tol), __fadd_rn(-fabsf(t3.y), -tol));
+    const float2 s = __fadd2_rn(__fadd2_rn(nb0, nb1), __fadd2_rn(nb2, nb3));
+    ok = ok & (s.x > -1152921504606846976.0f) & (s.y > -1152921504606846976.0f);     // guard of bilateral<true>
+    const float2 w0 = div2_fast_neg(make_float2(9.0f, 9.0f), nb0);
+    const float2 w1 = div2_fast_neg(make_float2(3.0f, 3.0f), nb1);
+    const float2 w2 = div2_fast_neg(make_float2(1.0f, 1.0f), nb2);
+    const float2 w3 = div2_fast_neg(make_float2(3.0f, 3.0f), nb3);
+    const float2 nfs2 = make_float2(nfs, nfs);
+    const float2 total = __fadd2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(w0, w1), w2), w3), nfs2);
+    const float2 wsum = __fadd2_rn(__ffma2_rn(la3, w3, __ffma2_rn(la2, w2, __ffma2_rn(la1, w1, __fmul2_rn(la0, w0)))), nfs2);
+    const float2 num = BLEND ? __fmul2_rn(ha, wsum) : wsum;
+    ok = ok & in_safe_range(total.x) & in_safe_range(total.y)
+            & ((num.x == 0.0f) | in_safe_range(num.x)) & ((num.y == 0.0f) | in_safe_range(num.y));
+    return div2_fast_neg(num, __fmul2_rn(total, m1));
+}
+
 template <bool BLEND, bool HI_HALF>
 __global__ void __launch_bounds__(kThreads)
 blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __grid_constant__ CUtensorMap lo_ao_map,
@@ -114,6 +159,27 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
     const int hx0 = blockIdx.x * kHW;
     const int hy0 = (a.row0 & ~1) + blockIdx.y * kHH;
     const int lx0 = (hx0 >> 1) - 3, ly0 = (hy0 >> 1) - 3;      // virtual low-res coordinate of raw tile (0,0)
+
+    // ---- this thread's 8 hi-res pixels (phase 4); their global loads are issued NOW so that the HBM/L2
+    //      latency hides behind the TMA wait and the three blur phases (the kernel was stalling on them)
+    // a warp takes rows w, w+8, w+16, w+24 of the tile: the row parity (which selects the operand order of
+    // UPS:229-232) is then warp-uniform and the parity branch of phase 4 never diverges
+    const int j = tid & 7, hy = ((tid >> 3) & 3) * 8 + (tid >> 5);
+    const int py = hy0 + hy, px0 = hx0 + 8 * j;
+    const bool active = !(py < a.row0 || py >= a.row1 || px0 >= a.hiw);
+    const bool full = (px0 + 8 <= a.hiw);
+    uint4 raw_d0 = make_uint4(0, 0, 0, 0), raw_d1 = make_uint4(0, 0, 0, 0);
+    uint2 raw_a = make_uint2(0, 0);
+    if (active && full) {
+        if (HI_HALF) {
+            raw_d0 = ldg_stream_u4(reinterpret_cast<const __half *>(a.hi_depth) + (size_t)py * a.hi_dpitch + px0);
+        } else {
+            const float *src = reinterpret_cast<const float *>(a.hi_depth) + (size_t)py * a.hi_dpitch + px0;
+            raw_d0 = ldg_stream_u4(src);
+            raw_d1 = ldg_stream_u4(src + 4);
+        }
+        if (BLEND) raw_a = ldg_stream_u2(a.hi_ao + (size_t)py * a.hi_apitch + px0);
+    }
 
     const bool interior = use_tma && lx0 >= 0 && ly0 >= 0 && (lx0 + kRawW <= a.low) && (ly0 + kRawH <= a.loh);
     if (interior) {
@@ -193,11 +259,7 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
     __syncthreads();
 
     // ---- bilateral upsample, UPS:213-232: thread -> 8 consecutive hi-res pixels of one row ----------
-    // a warp takes rows w, w+8, w+16, w+24 of the tile: the row parity (which selects the operand order of
-    // UPS:229-232) is then warp-uniform and the parity branch below never diverges
-    const int j = tid & 7, hy = ((tid >> 3) & 3) * 8 + (tid >> 5);
-    const int py = hy0 + hy, px0 = hx0 + 8 * j;
-    if (py < a.row0 || py >= a.row1 || px0 >= a.hiw) return;
+    if (!active) return;
 
     // blurred index of X-1 for the first pixel is 4j; quad rows: rY-1, rY with rY = ((hy+1)>>1)+1
     const int rY = ((hy + 1) >> 1) + 1;
@@ -215,13 +277,11 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
         lo_d[rr][0] = d0.x; lo_d[rr][1] = d0.y; lo_d[rr][2] = d1.x; lo_d[rr][3] = d1.y; lo_d[rr][4] = d2.x; lo_d[rr][5] = d2.y;
     }
 
-    const bool full = (px0 + 8 <= a.hiw);
     float hd[8], ha[8];
     if (HI_HALF) {
         const __half *src = reinterpret_cast<const __half *>(a.hi_depth) + (size_t)py * a.hi_dpitch + px0;
         if (full) {
-            const uint4 q = ldg_stream_u4(src);
-            const __half2 *h = reinterpret_cast<const __half2 *>(&q);
+            const __half2 *h = reinterpret_cast<const __half2 *>(&raw_d0);
 #pragma unroll
             for (int e = 0; e < 4; e++) { const float2 f = __half22float2(h[e]); hd[2 * e] = f.x; hd[2 * e + 1] = f.y; }
         } else {
@@ -231,7 +291,7 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
     } else {
         const float *src = reinterpret_cast<const float *>(a.hi_depth) + (size_t)py * a.hi_dpitch + px0;
         if (full) {
-            const float4 q0 = ldg_stream_f4(src), q1 = ldg_stream_f4(src + 4);
+            const float4 q0 = *reinterpret_cast<const float4 *>(&raw_d0), q1 = *reinterpret_cast<const float4 *>(&raw_d1);
             hd[0] = q0.x; hd[1] = q0.y; hd[2] = q0.z; hd[3] = q0.w; hd[4] = q1.x; hd[5] = q1.y; hd[6] = q1.z; hd[7] = q1.w;
         } else {
 #pragma unroll
@@ -241,7 +301,7 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
     if (BLEND) {
         const uint8_t *src = a.hi_ao + (size_t)py * a.hi_apitch + px0;
         if (full) {
-            const uint2 q = ldg_stream_u2(src);
+            const uint2 q = raw_a;
 #pragma unroll
             for (int e = 0; e < 4; e++) { ha[e] = unorm8_load((q.x >> (8 * e)) & 0xffu); ha[4 + e] = unorm8_load((q.y >> (8 * e)) & 0xffu); }
         } else {
@@ -274,7 +334,29 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
     }
     bool ok = a.fast_div_ok != 0;
     if (ok) {
-        if (y_odd) { MEAO_UPS_PIXELS(true, true, ok) } else { MEAO_UPS_PIXELS(true, false, ok) }
+        // packed fast path: pixel pairs (0,2) (1,3) (4,6) (5,7); blurred column of X-1 is m = (e+1)>>1
+#define MEAO_UPS_PAIR(E, YODD)                                                                                                  \
+        {                                                                                                                       \
+            constexpr int ma = ((E) + 1) >> 1, mb = ((E) + 3) >> 1;                                                             \
+            const float2 tl_d = make_float2(lo_d[0][ma], lo_d[0][mb]), tr_d = make_float2(lo_d[0][ma + 1], lo_d[0][mb + 1]);   \
+            const float2 bl_d = make_float2(lo_d[1][ma], lo_d[1][mb]), br_d = make_float2(lo_d[1][ma + 1], lo_d[1][mb + 1]);   \
+            const float2 tl_a = make_float2(bl_ao[0][ma], bl_ao[0][mb]), tr_a = make_float2(bl_ao[0][ma + 1], bl_ao[0][mb + 1]); \
+            const float2 bl_a = make_float2(bl_ao[1][ma], bl_ao[1][mb]), br_a = make_float2(bl_ao[1][ma + 1], bl_ao[1][mb + 1]); \
+            const float2 hd2 = make_float2(hd[E], hd[(E) + 2]), ha2 = make_float2(ha[E], ha[(E) + 2]);                          \
+            float2 r;                                                                                                           \
+            if (((E) & 1) != 0) {                                                                                               \
+                if (!(YODD)) r = bilateral2<BLEND>(hd2, ha2, bl_d, br_d, tr_d, tl_d, bl_a, br_a, tr_a, tl_a, tol, nfs, ok);     \
+                else         r = bilateral2<BLEND>(hd2, ha2, tl_d, bl_d, br_d, tr_d, tl_a, bl_a, br_a, tr_a, tol, nfs, ok);     \
+            } else {                                                                                                            \
+                if (!(YODD)) r = bilateral2<BLEND>(hd2, ha2, br_d, tr_d, tl_d, bl_d, br_a, tr_a, tl_a, bl_a, tol, nfs, ok);     \
+                else         r = bilateral2<BLEND>(hd2, ha2, tr_d, tl_d, bl_d, br_d, tr_a, tl_a, bl_a, br_a, tol, nfs, ok);     \
+            }                                                                                                                   \
+            code[E] = unorm8_code(r.x);                                                                                         \
+            code[(E) + 2] = unorm8_code(r.y);                                                                                   \
+        }
+        if (y_odd) { MEAO_UPS_PAIR(0, true) MEAO_UPS_PAIR(1, true) MEAO_UPS_PAIR(4, true) MEAO_UPS_PAIR(5, true) }
+        else       { MEAO_UPS_PAIR(0, false) MEAO_UPS_PAIR(1, false) MEAO_UPS_PAIR(4, false) MEAO_UPS_PAIR(5, false) }
+#undef MEAO_UPS_PAIR
     }
     if (!ok) {      // rare: inf / NaN / zero / denormal operands somewhere in this thread's 8 pixels -> plain IEEE operators
         bool unused = true;

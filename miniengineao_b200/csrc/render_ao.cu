@@ -34,67 +34,63 @@ constexpr int kWarps = kThreads / 32;
 static_assert((kSW * kSH / 4) % kThreads == 0, "tile must split evenly over the threads");
 static_assert(kSW == kRenderBoxW && kSH == kRenderBoxH, "TMA box mismatch");
 
-// Render.compute:60-75 for one sample pair; S1/S2 are the two mirrored taps.
-//   clamp(d, p, 1) == max(saturate(d), p) for p in [0,1], including d = NaN/+-inf (HLSL min/max
-//   return the non-NaN operand, saturate(NaN) = 0), so the result is bit-identical.
-__device__ __forceinline__ float pair_eval(float S1, float S2, float inv_range, float neg_front, float rf)
+// Render.compute:60-75 for one sample pair, TWO horizontally adjacent pixels at once (.x / .y lanes).
+//   * clamp(d, p, 1) == max(saturate(d), p) for p in [0,1], including d = NaN/+-inf (HLSL min/max return
+//     the non-NaN operand, saturate(NaN) = 0), so the result is bit-identical to the reference expression;
+//   * the kernel is issue-bound, so everything that has no .SAT / min-max flavour runs as packed f32x2
+//     (FFMA2 / FADD2 / FMUL2: two IEEE fp32 operations per lane per issue slot, lane-wise identical to the
+//     scalar instruction).
+__device__ __forceinline__ float2 pair_eval2(float2 S1, float2 S2, float2 inv_range, float2 neg_front, float rf)
 {
-    const float d1 = fmaf(S1, inv_range, neg_front);            // REN:65
-    const float d2 = fmaf(S2, inv_range, neg_front);            // REN:66
-    const float p1 = __saturatef(__fmul_rn(rf, d1));            // REN:68
-    const float p2 = __saturatef(__fmul_rn(rf, d2));            // REN:69
-    const float c1 = fmaxf(__saturatef(d1), p2);
-    const float c2 = fmaxf(__saturatef(d2), p1);
-    return __saturatef(fmaf(-p1, p2, __fadd_rn(c1, c2)));       // REN:71-74
+    const float2 d1 = __ffma2_rn(S1, inv_range, neg_front);             // REN:65
+    const float2 d2 = __ffma2_rn(S2, inv_range, neg_front);             // REN:66
+    const float p1x = __saturatef(__fmul_rn(rf, d1.x)), p1y = __saturatef(__fmul_rn(rf, d1.y));   // REN:68
+    const float p2x = __saturatef(__fmul_rn(rf, d2.x)), p2y = __saturatef(__fmul_rn(rf, d2.y));   // REN:69
+    const float2 c1 = make_float2(fmaxf(__saturatef(d1.x), p2x), fmaxf(__saturatef(d1.y), p2y));
+    const float2 c2 = make_float2(fmaxf(__saturatef(d2.x), p1x), fmaxf(__saturatef(d2.y), p1y));
+    const float2 sum = __fadd2_rn(c1, c2);
+    return make_float2(__saturatef(fmaf(-p1x, p2x, sum.x)), __saturatef(fmaf(-p1y, p2y, sum.y)));   // REN:71-74
 }
 
-// two adjacent pixels at once: c points at the (left) centre texel in the smem tile
+// c points at the (left) centre texel in the smem tile
 template <int DX, int DY>
-__device__ __forceinline__ void pair2(const float *c, float ir0, float ir1, float nf, float rf, float &r0, float &r1)
+__device__ __forceinline__ float2 pair2(const float *c, float2 ir, float2 nf, float rf)
 {
     constexpr int OFF = (4 * DY) * kSW + 4 * DX;
     const float2 s1 = *reinterpret_cast<const float2 *>(c + OFF);
     const float2 s2 = *reinterpret_cast<const float2 *>(c - OFF);
-    r0 = pair_eval(s1.x, s2.x, ir0, nf, rf);
-    r1 = pair_eval(s1.y, s2.y, ir1, nf, rf);
+    return pair_eval2(s1, s2, ir, nf, rf);
 }
 
 // Render.compute:87-93 (axial), x = N
 template <int N>
-__device__ __forceinline__ void axial2(const float *c, float inv0, float inv1, float it, float nf, float w, float rf, float &ao0, float &ao1)
+__device__ __forceinline__ void axial2(const float *c, float2 inv, float it, float nfs, float w, float rf, float2 &ao)
 {
-    const float ir0 = __fmul_rn(it, inv0), ir1 = __fmul_rn(it, inv1);     // REN:84
-    float a0, a1, b0, b1;
-    pair2<N, 0>(c, ir0, ir1, nf, rf, a0, a1);
-    pair2<0, N>(c, ir0, ir1, nf, rf, b0, b1);
-    ao0 = fmaf(w, __fmul_rn(0.5f, __fadd_rn(a0, b0)), ao0);
-    ao1 = fmaf(w, __fmul_rn(0.5f, __fadd_rn(a1, b1)), ao1);
+    const float2 ir = __fmul2_rn(make_float2(it, it), inv), nf = make_float2(nfs, nfs);      // REN:84
+    const float2 a = pair2<N, 0>(c, ir, nf, rf);
+    const float2 b = pair2<0, N>(c, ir, nf, rf);
+    ao = __ffma2_rn(make_float2(w, w), __fmul2_rn(make_float2(0.5f, 0.5f), __fadd2_rn(a, b)), ao);
 }
 // Render.compute:94-100 (diagonal), x == y == N: offsets x*TILE - x, x*TILE + x
 template <int N>
-__device__ __forceinline__ void diag2(const float *c, float inv0, float inv1, float it, float nf, float w, float rf, float &ao0, float &ao1)
+__device__ __forceinline__ void diag2(const float *c, float2 inv, float it, float nfs, float w, float rf, float2 &ao)
 {
-    const float ir0 = __fmul_rn(it, inv0), ir1 = __fmul_rn(it, inv1);
-    float a0, a1, b0, b1;
-    pair2<-N, N>(c, ir0, ir1, nf, rf, a0, a1);
-    pair2<N, N>(c, ir0, ir1, nf, rf, b0, b1);
-    ao0 = fmaf(w, __fmul_rn(0.5f, __fadd_rn(a0, b0)), ao0);
-    ao1 = fmaf(w, __fmul_rn(0.5f, __fadd_rn(a1, b1)), ao1);
+    const float2 ir = __fmul2_rn(make_float2(it, it), inv), nf = make_float2(nfs, nfs);
+    const float2 a = pair2<-N, N>(c, ir, nf, rf);
+    const float2 b = pair2<N, N>(c, ir, nf, rf);
+    ao = __ffma2_rn(make_float2(w, w), __fmul2_rn(make_float2(0.5f, 0.5f), __fadd2_rn(a, b)), ao);
 }
 // Render.compute:101-109 (L-shaped): y*T + x, y*T - x, x*T + y, x*T - y
 template <int X, int Y>
-__device__ __forceinline__ void lshape2(const float *c, float inv0, float inv1, float it, float nf, float w, float rf, float &ao0, float &ao1)
+__device__ __forceinline__ void lshape2(const float *c, float2 inv, float it, float nfs, float w, float rf, float2 &ao)
 {
-    const float ir0 = __fmul_rn(it, inv0), ir1 = __fmul_rn(it, inv1);
-    float a0, a1, b0, b1, c0, c1, d0, d1;
-    pair2<X, Y>(c, ir0, ir1, nf, rf, a0, a1);
-    pair2<-X, Y>(c, ir0, ir1, nf, rf, b0, b1);
-    pair2<Y, X>(c, ir0, ir1, nf, rf, c0, c1);
-    pair2<-Y, X>(c, ir0, ir1, nf, rf, d0, d1);
-    const float t0 = __fadd_rn(__fadd_rn(__fadd_rn(a0, b0), c0), d0);
-    const float t1 = __fadd_rn(__fadd_rn(__fadd_rn(a1, b1), c1), d1);
-    ao0 = fmaf(w, __fmul_rn(0.25f, t0), ao0);
-    ao1 = fmaf(w, __fmul_rn(0.25f, t1), ao1);
+    const float2 ir = __fmul2_rn(make_float2(it, it), inv), nf = make_float2(nfs, nfs);
+    const float2 a = pair2<X, Y>(c, ir, nf, rf);
+    const float2 b = pair2<-X, Y>(c, ir, nf, rf);
+    const float2 cc = pair2<Y, X>(c, ir, nf, rf);
+    const float2 d = pair2<-Y, X>(c, ir, nf, rf);
+    const float2 t = __fadd2_rn(__fadd2_rn(__fadd2_rn(a, b), cc), d);
+    ao = __ffma2_rn(make_float2(w, w), __fmul2_rn(make_float2(0.25f, 0.25f), t), ao);
 }
 
 __global__ void __launch_bounds__(kThreads, 8)
@@ -155,19 +151,20 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
         if (oy < a.row0 || oy >= a.row1 || ox >= a.lw) continue;
         const float *c = tile + (row + kAp) * kSW + (px + kAp);
         const float2 ctr = *reinterpret_cast<const float2 *>(c);
-        const float inv0 = rcp_ieee(ctr.x), inv1 = rcp_ieee(ctr.y);              // REN:140
-        float ao0 = 0.0f, ao1 = 0.0f;                                        // REN:142
+        const float2 inv = make_float2(rcp_ieee(ctr.x), rcp_ieee(ctr.y));      // REN:140
+        float2 ao = make_float2(0.0f, 0.0f);                                   // REN:142
         // REN:162-168 -- the 36-sample checker pattern, in call order
-        axial2<2>(c, inv0, inv1, a.inv_thickness[0], a.neg_front[0], a.weight[0], rf, ao0, ao1);
-        axial2<4>(c, inv0, inv1, a.inv_thickness[1], a.neg_front[1], a.weight[1], rf, ao0, ao1);
-        diag2<1>(c, inv0, inv1, a.inv_thickness[2], a.neg_front[2], a.weight[2], rf, ao0, ao1);
-        diag2<2>(c, inv0, inv1, a.inv_thickness[3], a.neg_front[3], a.weight[3], rf, ao0, ao1);
-        diag2<3>(c, inv0, inv1, a.inv_thickness[4], a.neg_front[4], a.weight[4], rf, ao0, ao1);
-        lshape2<1, 3>(c, inv0, inv1, a.inv_thickness[5], a.neg_front[5], a.weight[5], rf, ao0, ao1);
-        lshape2<2, 4>(c, inv0, inv1, a.inv_thickness[6], a.neg_front[6], a.weight[6], rf, ao0, ao1);
+        axial2<2>(c, inv, a.inv_thickness[0], a.neg_front[0], a.weight[0], rf, ao);
+        axial2<4>(c, inv, a.inv_thickness[1], a.neg_front[1], a.weight[1], rf, ao);
+        diag2<1>(c, inv, a.inv_thickness[2], a.neg_front[2], a.weight[2], rf, ao);
+        diag2<2>(c, inv, a.inv_thickness[3], a.neg_front[3], a.weight[3], rf, ao);
+        diag2<3>(c, inv, a.inv_thickness[4], a.neg_front[4], a.weight[4], rf, ao);
+        lshape2<1, 3>(c, inv, a.inv_thickness[5], a.neg_front[5], a.weight[5], rf, ao);
+        lshape2<2, 4>(c, inv, a.inv_thickness[6], a.neg_front[6], a.weight[6], rf, ao);
         // REN:176  lerp(1, ao, gIntensity) -> R8
-        const uint32_t k0 = unorm8_code(fmaf(a.intensity, __fadd_rn(ao0, -1.0f), 1.0f));
-        const uint32_t k1 = unorm8_code(fmaf(a.intensity, __fadd_rn(ao1, -1.0f), 1.0f));
+        const float2 le = __ffma2_rn(make_float2(a.intensity, a.intensity), __fadd2_rn(ao, make_float2(-1.0f, -1.0f)), make_float2(1.0f, 1.0f));
+        const uint32_t k0 = unorm8_code(le.x);
+        const uint32_t k1 = unorm8_code(le.y);
         uint8_t *dst = a.occ + (size_t)oy * a.opitch + ox;
         if (ox + 1 < a.lw) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(k0 | (k1 << 8));
         else dst[0] = (uint8_t)k0;
