@@ -123,6 +123,13 @@ int meao_render(MeaoCtx *ctx, const void *depth_dev, int32_t depth_kind, void *a
 /* Same with HOST buffers: H2D copy of depth, the ten passes, D2H copy of the AO texture, then a
  * stream synchronise.  Use meao_host_alloc for pinned memory. */
 int meao_render_host(MeaoCtx *ctx, const float *depth_host, int32_t depth_kind, uint8_t *ao_out_host);
+/* Pipelined form of meao_render_host for frame streams: enqueues H2D + kernels + D2H of one frame on staging slot
+ * `slot` (0 or 1) and returns; meao_host_wait(slot) blocks until that frame's AO is in ao_out_host.  Alternating the
+ * two slots overlaps the H2D copy of frame i+1 with the kernels and the D2H copy of frame i (the kernels of
+ * consecutive frames stay serialised: they share the context's intermediates).  Host buffers must be pinned
+ * (meao_host_alloc) for the copies to be asynchronous, and must stay valid until the matching wait. */
+int meao_render_host_async(MeaoCtx *ctx, const float *depth_host, int32_t depth_kind, uint8_t *ao_out_host, int32_t slot);
+int meao_host_wait(MeaoCtx *ctx, int32_t slot);
 int meao_synchronize(MeaoCtx *ctx);
 void *meao_host_alloc(size_t bytes);                /* cudaHostAlloc; NULL on failure */
 void meao_host_free(void *p);

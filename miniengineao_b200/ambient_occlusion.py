@@ -145,6 +145,29 @@ class AmbientOcclusion:
         self._check(self._lib.meao_render_host(self._ctx, d.ctypes.data, kind, out.ctypes.data))
         return out
 
+    def render_host_batch(self, depths, outs, *, linear: bool = False) -> None:
+        """Frame stream with HOST buffers: depths[i] (float32 [H, W]) -> outs[i] (uint8 [H, W]).  Frames alternate
+        over the two staging slots of the context, so the H2D copy of frame i+1 overlaps the kernels and the D2H
+        copy of frame i.  Pass pinned arrays (meao_host_alloc) for real overlap; the arrays must stay alive and
+        untouched until this call returns."""
+        self.LateUpdate()
+        rows = self._band_rows()
+        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        n = len(depths)
+        assert len(outs) == n
+        for i in range(n):
+            d, o = depths[i], outs[i]
+            if d.dtype != np.float32 or not d.flags.c_contiguous or d.shape != (rows, self._width):
+                raise ValueError("depths[i] must be C-contiguous float32 [rows, W]")
+            if o.dtype != np.uint8 or not o.flags.c_contiguous or o.shape != (rows, self._width):
+                raise ValueError("outs[i] must be C-contiguous uint8 [rows, W]")
+            slot = i & 1
+            if i >= 2:
+                self._check(self._lib.meao_host_wait(self._ctx, slot))
+            self._check(self._lib.meao_render_host_async(self._ctx, d.ctypes.data, kind, o.ctypes.data, slot))
+        self._check(self._lib.meao_host_wait(self._ctx, 0))
+        self._check(self._lib.meao_host_wait(self._ctx, 1))
+
     def synchronize(self) -> None:
         """Wait for the context's own stream (host-buffer path, debug copies) AND the current torch stream."""
         self._check(self._lib.meao_synchronize(self._ctx))

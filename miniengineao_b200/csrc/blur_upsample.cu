@@ -148,8 +148,11 @@ __device__ __forceinline__ float2 bilateral2(float2 hd, float2 ha,
     return div2_fast_neg(num, __fmul2_rn(total, m1));
 }
 
+#ifndef MEAO_UPS_MINB
+#define MEAO_UPS_MINB 5
+#endif
 template <bool BLEND, bool HI_HALF>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MEAO_UPS_MINB)
 blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __grid_constant__ CUtensorMap lo_ao_map,
                      const UpsampleArgs a, const int use_tma)
 {

@@ -81,9 +81,14 @@ struct MeaoCtx {
     uint8_t *occ[5] = {nullptr}; int occ_pitch[5] = {0};
     uint8_t *comb[4] = {nullptr};           // same pitch as occ of that level
     uint8_t *result = nullptr; int result_pitch = 0;
-    // staging for the host path
-    float *depth_stage = nullptr;           // device, W*H
-    uint8_t *ao_stage = nullptr;            // device, W*H
+    // staging for the host path: two slots so that the H2D copy of frame i+1 overlaps the kernels and the
+    // D2H copy of frame i (meao_render_host_async)
+    float *depth_stage[2] = {nullptr, nullptr};     // device, W*H each
+    uint8_t *ao_stage[2] = {nullptr, nullptr};      // device, W*H each
+    cudaStream_t slot_stream[2] = {nullptr, nullptr};
+    cudaEvent_t slot_done[2] = {nullptr, nullptr};
+    cudaEvent_t compute_done = nullptr;
+    bool compute_done_valid = false;
 
     bool tma_ok = false;
     CUtensorMap map_low_ren[5];             // LowDepth<k> with the render box
@@ -201,7 +206,8 @@ void free_buffers(MeaoCtx *c)
     drop_graph(c);
     if (c->arena) cudaFree(c->arena);
     c->arena = nullptr; c->arena_bytes = 0;
-    c->depth_stage = nullptr; c->ao_stage = nullptr;
+    c->depth_stage[0] = c->depth_stage[1] = nullptr; c->ao_stage[0] = c->ao_stage[1] = nullptr;
+    c->compute_done_valid = false;
 }
 
 int make_map(MeaoCtx *c, CUtensorMap *m, CUtensorMapDataType dt, int elem, void *base, int w, int h, int pitch_elems, int bw, int bh)
@@ -292,8 +298,8 @@ int allocate(MeaoCtx *c)
         o_occ[k] = take((size_t)c->occ_pitch[k] * c->lh[k]);
         if (k <= 3) o_comb[k] = take((size_t)c->occ_pitch[k] * c->lh[k]);
     }
-    size_t o_dst = take((size_t)W * H * sizeof(float));
-    size_t o_ast = take((size_t)W * H);
+    size_t o_dst[2], o_ast[2];
+    for (int i = 0; i < 2; i++) { o_dst[i] = take((size_t)W * H * sizeof(float)); o_ast[i] = take((size_t)W * H); }
     cudaError_t e = cudaMalloc(&c->arena, off);
     if (e != cudaSuccess) return fail(c, e == cudaErrorMemoryAllocation ? MEAO_ERR_NOMEM : MEAO_ERR_CUDA,
                                       "cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(e));
@@ -308,8 +314,7 @@ int allocate(MeaoCtx *c)
         c->occ[k] = (uint8_t *)(b + o_occ[k]);
         if (k <= 3) c->comb[k] = (uint8_t *)(b + o_comb[k]);
     }
-    c->depth_stage = (float *)(b + o_dst);
-    c->ao_stage = (uint8_t *)(b + o_ast);
+    for (int i = 0; i < 2; i++) { c->depth_stage[i] = (float *)(b + o_dst[i]); c->ao_stage[i] = (uint8_t *)(b + o_ast[i]); }
 
     c->tma_ok = false;
     if (c->encode) {
@@ -552,6 +557,9 @@ int meao_create(const MeaoDeviceCfg *cfg, MeaoCtx **out)
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&c->branch[i], cudaStreamNonBlocking);
     for (int i = 0; i < 5 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&c->slot_stream[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete c; return fail(nullptr, MEAO_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -578,6 +586,9 @@ void meao_destroy(MeaoCtx *c)
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto b : c->branch) if (b) cudaStreamDestroy(b);
     for (auto e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto b : c->slot_stream) if (b) { cudaStreamSynchronize(b); cudaStreamDestroy(b); }
+    for (auto e : c->slot_done) if (e) cudaEventDestroy(e);
+    if (c->compute_done) cudaEventDestroy(c->compute_done);
     delete c;
 }
 
@@ -766,16 +777,38 @@ int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void 
     return MEAO_OK;
 }
 
-int meao_render_host(MeaoCtx *c, const float *depth_host, int32_t kind, uint8_t *ao_host)
+int meao_render_host_async(MeaoCtx *c, const float *depth_host, int32_t kind, uint8_t *ao_host, int32_t slot)
 {
     int rc = ensure_ready(c); if (rc) return rc;
     if (!depth_host || !ao_host) return fail(c, MEAO_ERR_INVALID, "depth / ao_out is NULL");
+    if (slot != 0 && slot != 1) return fail(c, MEAO_ERR_INVALID, "slot must be 0 or 1");
     const size_t rows = (size_t)(c->band1 - c->band0);
-    CUDA_TRY(c, cudaMemcpyAsync(c->depth_stage, depth_host, rows * c->W * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = meao_render(c, c->depth_stage, kind, c->ao_stage, c->stream))) return rc;
-    CUDA_TRY(c, cudaMemcpyAsync(ao_host, c->ao_stage, rows * c->W, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaStream_t s = c->slot_stream[slot];
+    CUDA_TRY(c, cudaMemcpyAsync(c->depth_stage[slot], depth_host, rows * c->W * sizeof(float), cudaMemcpyHostToDevice, s));
+    // the two slots share the context's intermediates: kernels of consecutive frames are serialised, copies are not
+    if (c->compute_done_valid) CUDA_TRY(c, cudaStreamWaitEvent(s, c->compute_done, 0));
+    if ((rc = meao_render(c, c->depth_stage[slot], kind, c->ao_stage[slot], s))) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->compute_done, s));
+    c->compute_done_valid = true;
+    CUDA_TRY(c, cudaMemcpyAsync(ao_host, c->ao_stage[slot], rows * c->W, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(c, cudaEventRecord(c->slot_done[slot], s));
     return MEAO_OK;
+}
+
+int meao_host_wait(MeaoCtx *c, int32_t slot)
+{
+    if (!c || (slot != 0 && slot != 1)) return MEAO_ERR_INVALID;
+    if (c->plan_only) return MEAO_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->slot_stream[slot]));
+    return MEAO_OK;
+}
+
+int meao_render_host(MeaoCtx *c, const float *depth_host, int32_t kind, uint8_t *ao_host)
+{
+    int rc = meao_render_host_async(c, depth_host, kind, ao_host, 0);
+    if (rc) return rc;
+    return meao_host_wait(c, 0);
 }
 
 int meao_synchronize(MeaoCtx *c)
@@ -784,6 +817,7 @@ int meao_synchronize(MeaoCtx *c)
     if (c->plan_only) return MEAO_OK;
     CUDA_TRY(c, cudaSetDevice(c->device));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto st : c->slot_stream) CUDA_TRY(c, cudaStreamSynchronize(st));
     return MEAO_OK;
 }
 

@@ -29,6 +29,9 @@ constexpr int kTW = 64, kTH = 16;           // outputs per CTA (small tiles: 204
 constexpr int kAp = 16;                     // apron: 4 slice texels x stride 4
 constexpr int kSW = kTW + 2 * kAp;          // 96  == kRenderBoxW
 constexpr int kSH = kTH + 2 * kAp;          // 48  == kRenderBoxH
+#ifndef MEAO_REN_MINB
+#define MEAO_REN_MINB 8
+#endif
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
 static_assert((kSW * kSH / 4) % kThreads == 0, "tile must split evenly over the threads");
@@ -93,7 +96,7 @@ __device__ __forceinline__ void lshape2(const float *c, float2 inv, float it, fl
     ao = __ffma2_rn(make_float2(w, w), __fmul2_rn(make_float2(0.25f, 0.25f), t), ao);
 }
 
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, MEAO_REN_MINB)
 render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a, const int use_tma)
 {
 #ifdef MEAO_DEVICE_OK

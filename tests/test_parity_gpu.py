@@ -338,3 +338,27 @@ def test_fast_division_is_ieee_exact(torch_cuda):
     from miniengineao_b200 import AmbientOcclusion, Camera
     a = AmbientOcclusion(Camera(64, 64), device=0)
     assert a.selftest_div(1 << 30, seed=12345) == 0
+
+
+def test_pipelined_host_batch_matches_oracle(torch_cuda):
+    """meao_render_host_async / meao_host_wait (two staging slots): five distinct frames in flight, pinned buffers."""
+    import ctypes as C
+    from miniengineao_b200 import synth, _native as N
+    W, H = 640, 360
+    ao, orc = _mk(W, H, intensity=1.1)
+    lib = N.lib()
+    n = 5
+    ptrs = [(lib.meao_host_alloc(W * H * 4), lib.meao_host_alloc(W * H)) for _ in range(n)]
+    try:
+        ds = [np.ctypeslib.as_array(C.cast(p[0], C.POINTER(C.c_float)), shape=(H, W)) for p in ptrs]
+        os_ = [np.ctypeslib.as_array(C.cast(p[1], C.POINTER(C.c_uint8)), shape=(H, W)) for p in ptrs]
+        for i in range(n):
+            ds[i][...] = synth.lin01_to_raw(synth.random_depth(W, H, seed=100 + i))
+            os_[i][...] = 0
+        ao.render_host_batch(ds, os_)
+        for i in range(n):
+            assert np.array_equal(os_[i], orc.run(ds[i])), i
+    finally:
+        ao.close()
+        for p in ptrs:
+            lib.meao_host_free(p[0]); lib.meao_host_free(p[1])
