@@ -189,6 +189,13 @@ int meao_halo_unpack(MeaoCtx *ctx, int32_t side, const void *packed_dev, void *s
 int meao_render_band_prepare(MeaoCtx *ctx, const void *depth_band_dev, int32_t depth_kind, void *stream);
 int meao_render_band_finish(MeaoCtx *ctx, void *ao_band_out_dev, void *stream);
 
+/* The same split with the halo pack / unpack fused in and each half replayed as ONE CUDA graph:
+ *   phase A = prepare_depth on the band + pack of both outgoing halos (send_* may be NULL at the frame edge);
+ *   phase B = unpack of both incoming halos + Render x4 + Upsample x4.
+ * A band step is then: phase A, one neighbour send/recv per side (NCCL or peer copy), phase B. */
+int meao_band_phase_a(MeaoCtx *ctx, const void *depth_band_dev, int32_t depth_kind, void *send_up_dev, void *send_down_dev, void *stream);
+int meao_band_phase_b(MeaoCtx *ctx, const void *recv_up_dev, const void *recv_down_dev, void *ao_band_out_dev, void *stream);
+
 /* ---- command-buffer hook (Unity native-plugin style) -------------------------------------------- */
 /* replaces: camera.AddCommandBuffer(..., _renderCommand) (AO.cs:412-429): a host engine issues
  * CommandBuffer.IssuePluginEvent(meao_get_render_event_func(), event_id). */

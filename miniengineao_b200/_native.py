@@ -70,6 +70,8 @@ SIGNATURES = {
     "meao_halo_unpack": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "meao_render_band_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "meao_render_band_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "meao_band_phase_a": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "meao_band_phase_b": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "meao_bind_event": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "meao_render_event": (None, [C.c_int]),
     "meao_get_render_event_func": (RENDER_EVENT_FUNC, []),

@@ -285,6 +285,17 @@ class AmbientOcclusion:
     def band_finish(self, out_band, stream=None) -> None:
         self._check(self._lib.meao_render_band_finish(self._ctx, out_band.data_ptr(), self._stream(stream)))
 
+    def band_phase_a(self, depth_band, send_up, send_down, *, linear: bool = False, stream=None) -> None:
+        """prepare_depth on the band + pack of both halos, replayed as one CUDA graph."""
+        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        ptr = lambda t: (t.data_ptr() if t is not None and t.numel() else None)  # noqa: E731
+        self._check(self._lib.meao_band_phase_a(self._ctx, depth_band.data_ptr(), kind, ptr(send_up), ptr(send_down), self._stream(stream)))
+
+    def band_phase_b(self, recv_up, recv_down, out_band, stream=None) -> None:
+        """unpack of both halos + render x4 + upsample x4, replayed as one CUDA graph."""
+        ptr = lambda t: (t.data_ptr() if t is not None and t.numel() else None)  # noqa: E731
+        self._check(self._lib.meao_band_phase_b(self._ctx, ptr(recv_up), ptr(recv_down), out_band.data_ptr(), self._stream(stream)))
+
     # ---- introspection ----------------------------------------------------------------------------
     @property
     def launch_count(self) -> int:

@@ -81,7 +81,9 @@ cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int
 // ---- self test: div_fast / rcp_fast vs the IEEE operators on n random in-range operand pairs ------
 cudaError_t launch_selftest_div(uint64_t n, uint32_t seed, unsigned long long *mismatch_dev, cudaStream_t s);
 
-// ---- halo pack / unpack: rows [r0, r1) of a pitched buffer <-> contiguous staging --------------
-// (plain cudaMemcpy2DAsync is used; no kernel)
+// ---- halo pack / unpack: row blocks of pitched buffers <-> contiguous staging, one launch ------
+struct HaloSeg { const float *src; float *dst; int src_pitch, dst_pitch, width, rows; };
+struct HaloArgs { HaloSeg seg[8]; int nseg; };
+cudaError_t launch_halo_copy(const HaloArgs &a, cudaStream_t s);
 
 }  // namespace meao

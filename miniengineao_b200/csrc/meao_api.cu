@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -103,8 +104,9 @@ struct MeaoCtx {
     int64_t launches = 0;
 
     // CUDA graph cache: one instantiated graph per (depth, out, kind); dropped whenever the plan changes
-    struct GraphKey { const void *depth; void *out; int kind; bool operator<(const GraphKey &o) const {
-        return depth != o.depth ? depth < o.depth : (out != o.out ? out < o.out : kind < o.kind); } };
+    struct GraphKey { const void *p[4]; int kind; bool operator<(const GraphKey &o) const {
+        for (int i = 0; i < 4; i++) if (p[i] != o.p[i]) return p[i] < o.p[i];
+        return kind < o.kind; } };
     std::map<GraphKey, cudaGraphExec_t> graphs;
     void *last_out = nullptr;               // where the last final upsample wrote (nullptr: c->result)
     int last_kind = MEAO_DEPTH_RAW_F32;     // ingest kind of the last downsample (selects the atlas padding value)
@@ -422,11 +424,11 @@ int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
 // The same nine launches as record_frame, recorded as a DAG on forked streams (for graph capture): the four
 // render levels are independent, the coarse upsample chain 4->3->2 only needs Occlusion2..4,
 // and only the last two upsamples wait for the big level-1 render.
-int record_frame_dag(MeaoCtx *c, const void *depth, int kind, void *ao_out, cudaStream_t s)
+int record_frame_dag(MeaoCtx *c, const void *depth, int kind, void *ao_out, cudaStream_t s, bool do_prepare = true)
 {
     int rc;
     cudaStream_t b1 = c->branch[0], b2 = c->branch[1], b3 = c->branch[2];
-    if ((rc = record_downsample(c, depth, kind, s))) return rc;
+    if (do_prepare && (rc = record_downsample(c, depth, kind, s))) return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[0], s));
     CUDA_TRY(c, cudaStreamWaitEvent(b1, c->ev[0], 0));
     CUDA_TRY(c, cudaStreamWaitEvent(b2, c->ev[0], 0));
@@ -741,6 +743,85 @@ int meao_render_band_finish(MeaoCtx *c, void *ao_out, void *stream)
     return MEAO_OK;
 }
 
+static int halo_kernel(MeaoCtx *c, void *up, void *down, bool pack, cudaStream_t s)
+{
+    HaloArgs a{}; a.nseg = 0;
+    void *bufs[2] = {up, down};
+    for (int side = 0; side < 2; side++) {
+        if (!bufs[side]) continue;
+        Range r[5]; halo_ranges(c, side, pack, r);
+        float *p = (float *)bufs[side];
+        for (int k = 1; k <= 4; k++) {
+            const int rows = r[k].hi - r[k].lo;
+            if (rows <= 0) continue;
+            float *buf = c->low[k] + (size_t)r[k].lo * c->low_pitch[k];
+            HaloSeg &g = a.seg[a.nseg++];
+            if (pack) g = HaloSeg{buf, p, c->low_pitch[k], c->lw[k], c->lw[k], rows};
+            else      g = HaloSeg{p, buf, c->lw[k], c->low_pitch[k], c->lw[k], rows};
+            p += (size_t)rows * c->lw[k];
+        }
+    }
+    CUDA_TRY(c, launch_halo_copy(a, s));
+    if (a.nseg) c->launches++;
+    return 0;
+}
+
+// Graph-cached halves of a band step.  phase A: prepare_depth on the band + pack both halos (2 launches);
+// phase B: unpack both halos + 4 renders + 4 upsamples (9 launches, DAG).  The neighbour exchange happens between.
+static int band_graph(MeaoCtx *c, const MeaoCtx::GraphKey &key, cudaStream_t s, int nk, const std::function<int(cudaStream_t)> &record)
+{
+    if (c->flags & MEAO_FLAG_NO_GRAPH) return record(s);
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+        if (c->graphs.size() >= 64) drop_graph(c);
+        cudaGraph_t g = nullptr;
+        CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = c->launches;
+        int rc = record(c->stream);
+        c->launches = before;
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        cudaGraphExec_t ge = nullptr;
+        e = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        it = c->graphs.emplace(key, ge).first;
+    }
+    CUDA_TRY(c, cudaGraphLaunch(it->second, s));
+    c->launches += nk;
+    return 0;
+}
+
+int meao_band_phase_a(MeaoCtx *c, const void *depth, int32_t kind, void *send_up, void *send_down, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!depth) return fail(c, MEAO_ERR_INVALID, "depth is NULL");
+    c->last_kind = kind;
+    const MeaoCtx::GraphKey key{{depth, send_up, send_down, nullptr}, 100 + kind};
+    const int nk = 1 + ((send_up || send_down) ? 1 : 0);
+    return band_graph(c, key, (cudaStream_t)stream, nk, [&](cudaStream_t s) {
+        int r = record_downsample(c, depth, kind, s);
+        if (r) return r;
+        return halo_kernel(c, send_up, send_down, true, s);
+    });
+}
+
+int meao_band_phase_b(MeaoCtx *c, const void *recv_up, const void *recv_down, void *ao_out, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!ao_out) return fail(c, MEAO_ERR_INVALID, "ao_out is NULL");
+    const int kind = c->last_kind;
+    const MeaoCtx::GraphKey key{{recv_up, recv_down, ao_out, nullptr}, 200 + kind};
+    const int nk = 8 + ((recv_up || recv_down) ? 1 : 0);
+    c->last_out = ao_out;
+    return band_graph(c, key, (cudaStream_t)stream, nk, [&](cudaStream_t s) {
+        int r = halo_kernel(c, (void *)recv_up, (void *)recv_down, false, s);
+        if (r) return r;
+        return record_frame_dag(c, nullptr, kind, ao_out, s, false);
+    });
+}
+
 int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void *stream)
 {
     int rc = ensure_ready(c); if (rc) return rc;
@@ -753,7 +834,7 @@ int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void 
 
     // plan-once / replay: one captured graph per (depth, out, kind), like the reference's command buffer
     // that is re-recorded only when something changed (AO.cs:334-347)
-    const MeaoCtx::GraphKey key{depth, ao_out, kind};
+    const MeaoCtx::GraphKey key{{depth, ao_out, nullptr, nullptr}, kind};
     auto it = c->graphs.find(key);
     if (it == c->graphs.end()) {
         if (c->graphs.size() >= 64) drop_graph(c);

@@ -4,11 +4,11 @@ does not have -- SURVEY.md 8e).
 One process per GPU.  Rank r owns output rows [cuts[r], cuts[r+1]) (16-row aligned) and only ever sees that
 band of the raw depth.  Per frame:
 
-    band_prepare (own rows: LinearDepth + LowDepth1..4)
-      -> pack the border rows of LowDepth1..4 each neighbour needs      (meao_halo_pack, <= ~0.6 MB per side at 8K)
-      -> ONE send + ONE recv per neighbour                               (torch.distributed P2P: NCCL on GPUs, gloo in the CPU tests)
-      -> unpack into the same global-coordinate buffers                  (meao_halo_unpack)
-    band_finish (render x4 + upsample x4 on exactly the rows the band needs)
+    phase A  (one CUDA graph)  prepare_depth on the own rows (LinearDepth + LowDepth1..4)
+                               + pack of the border rows of LowDepth1..4 each neighbour needs (<= ~0.6 MB per side at 8K)
+    exchange                   ONE send + ONE recv per neighbour (torch.distributed P2P: NCCL on GPUs, gloo in the CPU tests)
+    phase B  (one CUDA graph)  unpack into the same global-coordinate buffers + render x4 + upsample x4 on exactly
+                               the rows the band needs
 
 The exchange is neighbour-only; no all-reduce / all-gather is ever needed.  The row ranges come from the C
 planner (meao_band_rows / meao_halo_rows), so this module contains no geometry of its own.
@@ -81,15 +81,9 @@ class RowTiledAO:
         """depth_band: CUDA f32 [rows, W]; out_band: CUDA u8 [rows, W].  Everything is enqueued on `stream`
         (default: torch's current stream), the P2P included, so steps can be issued back to back."""
         ao = self.ao
-        ao.band_prepare(depth_band, stream=stream)
-        for side in (0, 1):
-            if self.send[side].numel():
-                ao.halo_pack(side, self.send[side], stream=stream)
+        ao.band_phase_a(depth_band, self.send[0], self.send[1], stream=stream)       # graph: prepare_depth + pack
         exchange(self.send[0], self.send[1], self.recv[0], self.recv[1], self.rank, self.world)
-        for side in (0, 1):
-            if self.recv[side].numel():
-                ao.halo_unpack(side, self.recv[side], stream=stream)
-        ao.band_finish(out_band, stream=stream)
+        ao.band_phase_b(self.recv[0], self.recv[1], out_band, stream=stream)         # graph: unpack + 8 kernels (DAG)
 
 
 def halo_slices(rows: list[tuple[int, int]], widths: list[int]) -> list[tuple[int, int, int]]:

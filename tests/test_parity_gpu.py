@@ -362,3 +362,40 @@ def test_pipelined_host_batch_matches_oracle(torch_cuda):
         ao.close()
         for p in ptrs:
             lib.meao_host_free(p[0]); lib.meao_host_free(p[1])
+
+
+@pytest.mark.parametrize("W,H,bands", [(1920, 1080, 2), (3840, 2160, 4)])
+def test_graph_cached_band_phases_equal_whole_frame(torch_cuda, W, H, bands):
+    """meao_band_phase_a / meao_band_phase_b (pack / unpack fused in, each half one CUDA graph): same equality,
+    run twice so the second pass replays the cached graphs."""
+    from miniengineao_b200 import AmbientOcclusion, Camera, rowtile, synth
+    torch = torch_cuda
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    ref = AmbientOcclusion(Camera(W, H), device=0).render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    cuts = rowtile.partition(H, bands)
+    ctxs, send, recv = [], [], []
+    for i in range(bands):
+        a = AmbientOcclusion(Camera(W, H), device=0)
+        a.set_row_band(cuts[i], cuts[i + 1], *rowtile.neighbours(cuts, i))
+        ctxs.append(a)
+        mk = lambda n: torch.empty(int(n), dtype=torch.uint8, device="cuda")  # noqa: E731
+        send.append([mk(a.halo_bytes(0)), mk(a.halo_bytes(1))])
+        recv.append([mk(a.halo_recv_bytes(0)), mk(a.halo_recv_bytes(1))])
+    dts = [torch.from_numpy(depth[cuts[i]:cuts[i + 1]]).cuda() for i in range(bands)]
+    outs = [torch.zeros((cuts[i + 1] - cuts[i], W), dtype=torch.uint8, device="cuda") for i in range(bands)]
+    for _ in range(2):
+        for o in outs:
+            o.zero_()
+        for i, a in enumerate(ctxs):
+            a.band_phase_a(dts[i], send[i][0], send[i][1])
+        torch.cuda.synchronize()
+        for i in range(bands):          # the "exchange": what i sends down is what i+1 receives from above
+            if i + 1 < bands:
+                recv[i + 1][0].copy_(send[i][1])
+                recv[i][1].copy_(send[i + 1][0])
+        torch.cuda.synchronize()
+        for i, a in enumerate(ctxs):
+            a.band_phase_b(recv[i][0], recv[i][1], outs[i])
+        torch.cuda.synchronize()
+        got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+        assert int((got != ref).sum()) == 0
