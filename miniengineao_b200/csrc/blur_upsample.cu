@@ -54,24 +54,6 @@ struct __align__(128) Smem {
     alignas(8) uint64_t bar;
 };
 
-// Upsample.compute:74-81.  /2 and /4 are exact scalings.
-__device__ __forceinline__ float smart_blur(float a, float b, float c, float d, float e, bool Left, bool Middle, bool Right)
-{
-    b = (Left | Middle) ? b : c;
-    a = Left ? a : b;
-    d = (Right | Middle) ? d : c;
-    e = Right ? e : d;
-    const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(a, e), 0.5f), b), c), d);
-    return __fmul_rn(s, 0.25f);
-}
-
-// Upsample.compute:83-87
-__device__ __forceinline__ bool compare_deltas(float d1, float d2, float l1, float l2, float step, float kblur)
-{
-    const float temp = fmaf(d1, d2, step);
-    return __fmul_rn(temp, temp) > __fmul_rn(__fmul_rn(l1, l2), kblur);
-}
-
 // Upsample.compute:177-183 with the swizzled argument order of :229-232.
 // FAST: the five divisions use div_fast (common.cuh) and `ok` collects the validity guard of the whole
 // group; when it ends up false the caller recomputes with FAST = false (plain IEEE operators).
@@ -101,6 +83,42 @@ __device__ __forceinline__ float bilateral(float hi_depth, float hi_ao,
         return div_fast(num, total);
     }
     return num / total;
+}
+
+// ---- packed (two-lane) 5-tap depth-aware blur -------------------------------------------------
+// The two lanes are two independent rows (horizontal pass) or two independent columns (vertical pass);
+// each lane performs exactly CompareDeltas (Upsample.compute:83-87) and SmartBlur (:74-81; /2 and /4 are exact scalings).
+__device__ __forceinline__ void compare_deltas2(float2 d1, float2 d2, float2 l1, float2 l2, float2 step2, float2 kblur2, bool &cx, bool &cy)
+{
+    const float2 temp = __ffma2_rn(d1, d2, step2);
+    const float2 tt = __fmul2_rn(temp, temp);
+    const float2 lk = __fmul2_rn(__fmul2_rn(l1, l2), kblur2);
+    cx = tt.x > lk.x; cy = tt.y > lk.y;
+}
+__device__ __forceinline__ float2 smart_blur2(float2 a, float2 b, float2 c, float2 d, float2 e,
+                                              bool Lx, bool Mx, bool Rx, bool Ly, bool My, bool Ry)
+{
+    b.x = (Lx | Mx) ? b.x : c.x;  b.y = (Ly | My) ? b.y : c.y;
+    a.x = Lx ? a.x : b.x;         a.y = Ly ? a.y : b.y;
+    d.x = (Rx | Mx) ? d.x : c.x;  d.y = (Ry | My) ? d.y : c.y;
+    e.x = Rx ? e.x : d.x;         e.y = Ry ? e.y : d.y;
+    const float2 s = __fadd2_rn(__fadd2_rn(__fadd2_rn(__fmul2_rn(__fadd2_rn(a, e), make_float2(0.5f, 0.5f)), b), c), d);
+    return __fmul2_rn(s, make_float2(0.25f, 0.25f));
+}
+// N outputs from N + 4 taps per lane
+template <int N>
+__device__ __forceinline__ void blur_run2(const float2 (&av)[N + 4], const float2 (&dv)[N + 4], float step, float kblur, float2 (&out)[N])
+{
+    const float2 m1 = make_float2(-1.0f, -1.0f), step2 = make_float2(step, step), k2 = make_float2(kblur, kblur);
+    float2 dd[N + 3], ll[N + 3];
+    bool cx[N + 2], cy[N + 2];
+#pragma unroll
+    for (int i = 0; i < N + 3; i++) { dd[i] = __ffma2_rn(dv[i], m1, dv[i + 1]); ll[i] = __ffma2_rn(dd[i], dd[i], step2); }   // d[i+1] - d[i]
+#pragma unroll
+    for (int i = 0; i < N + 2; i++) compare_deltas2(dd[i], dd[i + 1], ll[i], ll[i + 1], step2, k2, cx[i], cy[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+        out[i] = smart_blur2(av[i], av[i + 1], av[i + 2], av[i + 3], av[i + 4], cx[i], cx[i + 1], cx[i + 2], cy[i], cy[i + 1], cy[i + 2]);
 }
 
 // ---- packed-f32x2 fast path -------------------------------------------------------------------
@@ -194,70 +212,72 @@ blur_upsample_kernel(const __grid_constant__ CUtensorMap lo_depth_map, const __g
             tma_load_2d(sm.box_ao, &lo_ao_map, lx0 - kBoxAOff, ly0, &sm.bar);
         }
         mbar_wait(&sm.bar, 0);
-        for (int idx = tid; idx < kRawH * kRawP; idx += kThreads) {
-            const int r = idx / kRawP, c = idx - r * kRawP;
-            const float d = (c + kBoxDOff < kBoxDP) ? sm.box_depth[r * kBoxDP + c + kBoxDOff] : 1.0f;   // column 39 is never consumed
-            sm.lo_depth[r * kLoDP + c] = d;
-            sm.inv_depth[r * kRawP + c] = rcp_ieee(d);                                       // UPS:67
-            sm.ao[r * kRawP + c] = unorm8_load(sm.box_ao[r * kBoxAP + c + kBoxAOff]);
+    }
+    // ---- phase 1: 22 rows x 10 groups of 4 texels: inverse depth (UPS:67) and AO codes -> float (UPS:56)
+    if (tid < kRawH * 10) {
+        const int r = tid / 10, c0 = (tid - r * 10) * 4;
+        float d[4]; uint32_t k[4];
+        if (interior) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                d[i] = (c0 + i + kBoxDOff < kBoxDP) ? sm.box_depth[r * kBoxDP + c0 + i + kBoxDOff] : 1.0f;   // column 39 is never consumed
+                k[i] = sm.box_ao[r * kBoxAP + c0 + i + kBoxAOff];
+            }
+        } else {    // border tile: point + clamp addressing (UPS:56,67)
+            const int sy = iclamp(ly0 + r, 0, a.loh - 1);
+            const float *drow = a.lo_depth + (size_t)sy * a.lo_dpitch;
+            const uint8_t *arow = a.lo_ao + (size_t)sy * a.lo_apitch;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int sx = iclamp(lx0 + c0 + i, 0, a.low - 1);
+                d[i] = __ldg(drow + sx);
+                k[i] = __ldg(arow + sx);
+            }
         }
-    } else {
-        // border tile: point + clamp addressing (UPS:56,67)
-        for (int idx = tid; idx < kRawH * kRawP; idx += kThreads) {
-            const int r = idx / kRawP, c = idx - r * kRawP;
-            const int sx = iclamp(lx0 + c, 0, a.low - 1), sy = iclamp(ly0 + r, 0, a.loh - 1);
-            const float d = __ldg(a.lo_depth + (size_t)sy * a.lo_dpitch + sx);
-            sm.lo_depth[r * kLoDP + c] = d;
-            sm.inv_depth[r * kRawP + c] = rcp_ieee(d);
-            sm.ao[r * kRawP + c] = unorm8_load(__ldg(a.lo_ao + (size_t)sy * a.lo_apitch + sx));
-        }
+        *reinterpret_cast<float2 *>(&sm.lo_depth[r * kLoDP + c0]) = make_float2(d[0], d[1]);
+        *reinterpret_cast<float2 *>(&sm.lo_depth[r * kLoDP + c0 + 2]) = make_float2(d[2], d[3]);
+        *reinterpret_cast<float4 *>(&sm.inv_depth[r * kRawP + c0]) = make_float4(rcp_ieee(d[0]), rcp_ieee(d[1]), rcp_ieee(d[2]), rcp_ieee(d[3]));
+        *reinterpret_cast<float4 *>(&sm.ao[r * kRawP + c0]) = make_float4(unorm8_load(k[0]), unorm8_load(k[1]), unorm8_load(k[2]), unorm8_load(k[3]));
     }
     __syncthreads();
 
     const float step = a.step_size, kblur = a.blur_tolerance;
 
-    // ---- horizontal blur, UPS:89-130: 22 rows x 9 runs of 4 outputs; output c is centred on raw c+2
-    if (tid < kRawH * 9) {
-        const int r = tid / 9, c0 = (tid - r * 9) * 4;
-        const float4 A0 = *reinterpret_cast<const float4 *>(&sm.ao[r * kRawP + c0]);
-        const float4 A1 = *reinterpret_cast<const float4 *>(&sm.ao[r * kRawP + c0 + 4]);
-        const float4 D0 = *reinterpret_cast<const float4 *>(&sm.inv_depth[r * kRawP + c0]);
-        const float4 D1 = *reinterpret_cast<const float4 *>(&sm.inv_depth[r * kRawP + c0 + 4]);
-        const float av[8] = {A0.x, A0.y, A0.z, A0.w, A1.x, A1.y, A1.z, A1.w};
-        const float dv[8] = {D0.x, D0.y, D0.z, D0.w, D1.x, D1.y, D1.z, D1.w};
-        float dd[7], ll[7];
-        bool cc[6];
+    // ---- horizontal blur, UPS:89-130: 11 row pairs (the two packed lanes) x 9 runs of 4 outputs;
+    //      output c is centred on raw column c+2
+    if (tid < (kRawH / 2) * 9) {
+        const int rp = tid / 9, c0 = (tid - rp * 9) * 4, r = 2 * rp;
+        float2 av[8], dv[8], o[4];
 #pragma unroll
-        for (int i = 0; i < 7; i++) { dd[i] = __fadd_rn(dv[i + 1], -dv[i]); ll[i] = fmaf(dd[i], dd[i], step); }
-#pragma unroll
-        for (int i = 0; i < 6; i++) cc[i] = compare_deltas(dd[i], dd[i + 1], ll[i], ll[i + 1], step, kblur);
-        float4 o;
-        o.x = smart_blur(av[0], av[1], av[2], av[3], av[4], cc[0], cc[1], cc[2]);
-        o.y = smart_blur(av[1], av[2], av[3], av[4], av[5], cc[1], cc[2], cc[3]);
-        o.z = smart_blur(av[2], av[3], av[4], av[5], av[6], cc[2], cc[3], cc[4]);
-        o.w = smart_blur(av[3], av[4], av[5], av[6], av[7], cc[3], cc[4], cc[5]);
-        *reinterpret_cast<float4 *>(&sm.hblur[r * kBlurP + c0]) = o;
+        for (int q = 0; q < 2; q++) {
+            const float4 A0 = *reinterpret_cast<const float4 *>(&sm.ao[r * kRawP + c0 + 4 * q]);
+            const float4 A1 = *reinterpret_cast<const float4 *>(&sm.ao[(r + 1) * kRawP + c0 + 4 * q]);
+            const float4 D0 = *reinterpret_cast<const float4 *>(&sm.inv_depth[r * kRawP + c0 + 4 * q]);
+            const float4 D1 = *reinterpret_cast<const float4 *>(&sm.inv_depth[(r + 1) * kRawP + c0 + 4 * q]);
+            av[4 * q] = make_float2(A0.x, A1.x); av[4 * q + 1] = make_float2(A0.y, A1.y);
+            av[4 * q + 2] = make_float2(A0.z, A1.z); av[4 * q + 3] = make_float2(A0.w, A1.w);
+            dv[4 * q] = make_float2(D0.x, D1.x); dv[4 * q + 1] = make_float2(D0.y, D1.y);
+            dv[4 * q + 2] = make_float2(D0.z, D1.z); dv[4 * q + 3] = make_float2(D0.w, D1.w);
+        }
+        blur_run2<4>(av, dv, step, kblur, o);
+        *reinterpret_cast<float4 *>(&sm.hblur[r * kBlurP + c0]) = make_float4(o[0].x, o[1].x, o[2].x, o[3].x);
+        *reinterpret_cast<float4 *>(&sm.hblur[(r + 1) * kBlurP + c0]) = make_float4(o[0].y, o[1].y, o[2].y, o[3].y);
     }
     __syncthreads();
 
-    // ---- vertical blur, UPS:132-170: 34 columns x 6 runs of 3 outputs; output r centred on row r+2,
-    //      depth column offset +2 (UPS:141-146)
-    if (tid < kBlurW * 6) {
-        const int run = tid / kBlurW, c = tid - run * kBlurW, r0 = run * 3;
-        float av[7], dv[7], dd[6], ll[6];
-        bool cc[5];
+    // ---- vertical blur, UPS:132-170: 17 column pairs (the two packed lanes) x 3 runs of 6 outputs;
+    //      output r centred on row r+2, depth column offset +2 (UPS:141-146)
+    if (tid < (kBlurW / 2) * 3) {
+        const int run = tid / (kBlurW / 2), c = 2 * (tid - run * (kBlurW / 2)), r0 = run * 6;
+        float2 av[10], dv[10], o[6];
 #pragma unroll
-        for (int i = 0; i < 7; i++) {
-            av[i] = sm.hblur[(r0 + i) * kBlurP + c];
-            dv[i] = sm.inv_depth[(r0 + i) * kRawP + c + 2];
+        for (int i = 0; i < 10; i++) {
+            av[i] = *reinterpret_cast<const float2 *>(&sm.hblur[(r0 + i) * kBlurP + c]);
+            dv[i] = *reinterpret_cast<const float2 *>(&sm.inv_depth[(r0 + i) * kRawP + c + 2]);
         }
+        blur_run2<6>(av, dv, step, kblur, o);
 #pragma unroll
-        for (int i = 0; i < 6; i++) { dd[i] = __fadd_rn(dv[i + 1], -dv[i]); ll[i] = fmaf(dd[i], dd[i], step); }
-#pragma unroll
-        for (int i = 0; i < 5; i++) cc[i] = compare_deltas(dd[i], dd[i + 1], ll[i], ll[i + 1], step, kblur);
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            sm.vblur[(r0 + i) * kBlurP + c] = smart_blur(av[i], av[i + 1], av[i + 2], av[i + 3], av[i + 4], cc[i], cc[i + 1], cc[i + 2]);
+        for (int i = 0; i < 6; i++) *reinterpret_cast<float2 *>(&sm.vblur[(r0 + i) * kBlurP + c]) = o[i];
     }
     __syncthreads();
 
