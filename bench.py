@@ -332,6 +332,29 @@ def run_ours(args) -> None:
                     "pipe_frac": round(total_alg * K / (ms_max * 1e-3) / 1e9 / peak, 4),
                     "kernel_share_of_step": round(means[dom] / sum(means.values()), 4)}
 
+    # ---- the consumer end: frame-buffer composite, a genuinely HBM-bound kernel -------------------
+    composite = None
+    if rank == 0:
+        peak, _ = load_peaks()
+        comp = {}
+        for name, dt_, bpp in (("rgba16f", torch.float16, 8), ("rgba8", torch.uint8, 4)):
+            bufs = [torch.zeros((H, W, 4), dtype=dt_, device=dev) for _ in range(6)]     # 6 x 66 MB > L2 for rgba16f
+            for b_ in bufs:
+                ao.composite_framebuffer(outs[0], b_)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 30
+            c0.record()
+            for i in range(reps):
+                ao.composite_framebuffer(outs[i % NBUF], bufs[i % 6])
+            c1.record()
+            torch.cuda.synchronize()
+            us = c0.elapsed_time(c1) / reps * 1e3
+            nbytes = W * H * (2 * bpp + 1)
+            comp[name] = {"us": round(us, 2), "bytes": nbytes, "gbs": round(nbytes / us / 1e3, 1), "frac_of_peak": round(nbytes / us / 1e3 / peak, 3)}
+            del bufs
+        composite = {"kernel": "composite_framebuffer (Blit.shader pass 2: colour *= ao), read + write colour + read ao", **comp}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -359,7 +382,7 @@ def run_ours(args) -> None:
                 "e2e": {"value": round(e2e_value, 1), "unit": "Mpixels/s", "h2d_bytes_per_step": W * H * 4, "d2h_bytes_per_step": W * H, "steps": Ke,
                         "api": "AmbientOcclusion.render_host_batch -> meao_render_host_async / meao_host_wait (pinned host buffers, 2 staging slots)",
                         "serial_value": round(e2e_serial, 1)},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "rowtile": rowtile}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "rowtile": rowtile, "composite": composite}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

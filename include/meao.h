@@ -72,7 +72,11 @@ typedef struct {
 
 typedef enum {
     MEAO_DEPTH_RAW_F32 = 0,     /* camera depth, linearised by Downsample1.compute:37-48 (reference behaviour) */
-    MEAO_DEPTH_LINEAR_F32 = 1   /* already-linear depth (Linearize becomes the identity; not in the reference) */
+    MEAO_DEPTH_LINEAR_F32 = 1,  /* already-linear depth (Linearize becomes the identity; not in the reference) */
+    /* native depth-buffer formats (what Blit.shader pass 0 :48-64 samples): the UNORM code is
+     * converted with the D3D rule (float)code * (1 / (2^n - 1)) and then linearised like RAW_F32 */
+    MEAO_DEPTH_RAW_D16_UNORM = 2,   /* uint16 codes, 2 bytes / pixel */
+    MEAO_DEPTH_RAW_D24S8 = 3        /* uint32 words, depth in the low 24 bits (D24_UNORM_S8_UINT), stencil ignored */
 } MeaoDepthKind;
 
 /* Debug buffer ids, numbering of AmbientOcclusion.cs:787-808. */
@@ -122,13 +126,13 @@ int meao_resize(MeaoCtx *ctx, int32_t width, int32_t height);
 int meao_render(MeaoCtx *ctx, const void *depth_dev, int32_t depth_kind, void *ao_out_dev, void *stream);
 /* Same with HOST buffers: H2D copy of depth, the ten passes, D2H copy of the AO texture, then a
  * stream synchronise.  Use meao_host_alloc for pinned memory. */
-int meao_render_host(MeaoCtx *ctx, const float *depth_host, int32_t depth_kind, uint8_t *ao_out_host);
+int meao_render_host(MeaoCtx *ctx, const void *depth_host, int32_t depth_kind, uint8_t *ao_out_host);
 /* Pipelined form of meao_render_host for frame streams: enqueues H2D + kernels + D2H of one frame on staging slot
  * `slot` (0 or 1) and returns; meao_host_wait(slot) blocks until that frame's AO is in ao_out_host.  Alternating the
  * two slots overlaps the H2D copy of frame i+1 with the kernels and the D2H copy of frame i (the kernels of
  * consecutive frames stay serialised: they share the context's intermediates).  Host buffers must be pinned
  * (meao_host_alloc) for the copies to be asynchronous, and must stay valid until the matching wait. */
-int meao_render_host_async(MeaoCtx *ctx, const float *depth_host, int32_t depth_kind, uint8_t *ao_out_host, int32_t slot);
+int meao_render_host_async(MeaoCtx *ctx, const void *depth_host, int32_t depth_kind, uint8_t *ao_out_host, int32_t slot);
 int meao_host_wait(MeaoCtx *ctx, int32_t slot);
 int meao_synchronize(MeaoCtx *ctx);
 void *meao_host_alloc(size_t bytes);                /* cudaHostAlloc; NULL on failure */
@@ -195,6 +199,20 @@ int meao_render_band_finish(MeaoCtx *ctx, void *ao_band_out_dev, void *stream);
  * A band step is then: phase A, one neighbour send/recv per side (NCCL or peer copy), phase B. */
 int meao_band_phase_a(MeaoCtx *ctx, const void *depth_band_dev, int32_t depth_kind, void *send_up_dev, void *send_down_dev, void *stream);
 int meao_band_phase_b(MeaoCtx *ctx, const void *recv_up_dev, const void *recv_down_dev, void *ao_band_out_dev, void *stream);
+
+/* ---- composite: the consumer end of the pipe ------------------------------------------- */
+typedef enum {
+    MEAO_FMT_RGBA8_UNORM = 0,   /* ARGB32-class LDR target, 4 bytes / pixel */
+    MEAO_FMT_RGBA16_FLOAT = 1   /* ARGBHalf HDR target, 8 bytes / pixel */
+} MeaoColorFormat;
+/* replaces: PushCompositeCommands, frame-buffer branch (AO.cs:835-838) = Blit.shader pass 2 (:84-101),
+ * "Blend Zero SrcAlpha" with src = ao.rrrr:   color.rgba *= ao.   ao_dev: width*height R8 codes (tight rows, what
+ * meao_render wrote); color_dev: width*height pixels, tight rows, updated in place.  16-byte aligned pointers. */
+int meao_composite_framebuffer(MeaoCtx *ctx, const void *ao_dev, void *color_dev, int32_t color_format, void *stream);
+/* replaces: PushCompositeCommands, ambient-only deferred branch (AO.cs:830-834) = Blit.shader pass 1 (:66-92),
+ * "Blend Zero OneMinusSrcColor, Zero OneMinusSrcAlpha" with src0 = (0,0,0,1-ao), src1 = (1-ao,1-ao,1-ao,0):
+ *   gbuffer0.a *= 1-(1-ao)  (RGBA8, occlusion channel),  gbuffer3.rgb *= 1-(1-ao)  (ambient/emission target). */
+int meao_composite_gbuffer(MeaoCtx *ctx, const void *ao_dev, void *gbuffer0_rgba8_dev, void *gbuffer3_dev, int32_t gbuffer3_format, void *stream);
 
 /* ---- command-buffer hook (Unity native-plugin style) -------------------------------------------- */
 /* replaces: camera.AddCommandBuffer(..., _renderCommand) (AO.cs:412-429): a host engine issues

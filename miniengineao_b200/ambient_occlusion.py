@@ -116,32 +116,46 @@ class AmbientOcclusion:
         return rebuild or resized
 
     # ---- frame ----------------------------------------------------------------------------------
+    @staticmethod
+    def _kind(dtype_name: str, linear: bool) -> int:
+        """float32 -> RAW_F32 (or LINEAR_F32); uint16 -> D16_UNORM codes; int32 / uint32 -> D24_UNORM_S8_UINT words."""
+        if dtype_name == "float32":
+            return N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        if linear:
+            raise ValueError("linear depth must be float32")
+        if dtype_name == "uint16":
+            return N.MEAO_DEPTH_RAW_D16_UNORM
+        if dtype_name in ("int32", "uint32"):
+            return N.MEAO_DEPTH_RAW_D24S8
+        raise ValueError(f"unsupported depth dtype {dtype_name}")
+
     def render(self, depth, out=None, *, linear: bool = False, stream=None):
-        """depth: CUDA float32 tensor [H, W] (raw camera depth, or linear if linear=True).
-        Returns a CUDA uint8 tensor [H, W] -- the AmbientOcclusion R8 texture (AO.cs:475)."""
+        """depth: CUDA tensor [H, W]: float32 raw camera depth (or linear if linear=True), uint16 D16_UNORM codes,
+        or int32 D24_UNORM_S8_UINT words.  Returns a CUDA uint8 tensor [H, W] -- the AmbientOcclusion R8 texture (AO.cs:475)."""
         import torch
         self.LateUpdate()
-        if not (depth.is_cuda and depth.dtype == torch.float32 and depth.is_contiguous()):
-            raise ValueError("depth must be a contiguous CUDA float32 tensor")
+        if not (depth.is_cuda and depth.is_contiguous()):
+            raise ValueError("depth must be a contiguous CUDA tensor")
         rows = self._band_rows()
         if tuple(depth.shape) != (rows, self._width):
             raise ValueError(f"depth shape {tuple(depth.shape)} != {(rows, self._width)}")
         if out is None:
             out = torch.empty((rows, self._width), dtype=torch.uint8, device=depth.device)
-        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        kind = self._kind(str(depth.dtype).replace("torch.", ""), linear)
         self._check(self._lib.meao_render(self._ctx, depth.data_ptr(), kind, out.data_ptr(), self._stream(stream)))
         return out
 
     def render_host(self, depth: np.ndarray, out: np.ndarray | None = None, *, linear: bool = False) -> np.ndarray:
-        """Host float32 [H, W] in, host uint8 [H, W] out (H2D + ten passes + D2H + sync)."""
+        """Host [H, W] depth (float32 / uint16 D16 codes / uint32 D24S8 words) in, host uint8 [H, W] out
+        (H2D + the kernels + D2H + sync)."""
         self.LateUpdate()
         rows = self._band_rows()
-        d = np.ascontiguousarray(depth, dtype=np.float32)
+        d = np.ascontiguousarray(depth)
         if d.shape != (rows, self._width):
             raise ValueError(f"depth shape {d.shape} != {(rows, self._width)}")
         if out is None:
             out = np.empty((rows, self._width), np.uint8)
-        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
+        kind = self._kind(d.dtype.name, linear)
         self._check(self._lib.meao_render_host(self._ctx, d.ctypes.data, kind, out.ctypes.data))
         return out
 
@@ -167,6 +181,20 @@ class AmbientOcclusion:
             self._check(self._lib.meao_render_host_async(self._ctx, d.ctypes.data, kind, o.ctypes.data, slot))
         self._check(self._lib.meao_host_wait(self._ctx, 0))
         self._check(self._lib.meao_host_wait(self._ctx, 1))
+
+    # ---- composite (Blit.shader passes 1 / 2, AO.cs:822-839) -------------------------------------------
+    def composite_framebuffer(self, ao, color, *, stream=None) -> None:
+        """color (CUDA uint8 [H, W, 4] = RGBA8, or float16 [H, W, 4] = RGBA16F) *= ao, in place (pass 2)."""
+        import torch
+        fmt = N.MEAO_FMT_RGBA16_FLOAT if color.dtype == torch.float16 else N.MEAO_FMT_RGBA8_UNORM
+        self._check(self._lib.meao_composite_framebuffer(self._ctx, ao.data_ptr(), color.data_ptr(), fmt, self._stream(stream)))
+
+    def composite_gbuffer(self, ao, gbuffer0, gbuffer3, *, stream=None) -> None:
+        """gbuffer0 (RGBA8).a *= 1-(1-ao); gbuffer3 (RGBA8 or RGBA16F).rgb *= 1-(1-ao), in place (pass 1)."""
+        import torch
+        fmt = N.MEAO_FMT_RGBA16_FLOAT if gbuffer3.dtype == torch.float16 else N.MEAO_FMT_RGBA8_UNORM
+        self._check(self._lib.meao_composite_gbuffer(self._ctx, ao.data_ptr(), gbuffer0.data_ptr(), gbuffer3.data_ptr(), fmt,
+                                                     self._stream(stream)))
 
     def synchronize(self) -> None:
         """Wait for the context's own stream (host-buffer path, debug copies) AND the current torch stream."""

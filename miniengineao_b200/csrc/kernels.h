@@ -16,7 +16,8 @@ namespace meao {
 
 // ---- stage 1: prepare_depth = Downsample1.compute + Downsample2.compute fused ----------------
 struct PrepareArgs {
-    const float *depth;     // input rows [depth_row0, ...) of the frame, row pitch = W floats
+    const void *depth;      // input rows [depth_row0, ...) of the frame, row pitch = W elements (f32 / u16 / u32)
+    int in_format;          // 0 = f32, 1 = D16_UNORM codes (u16), 2 = D24_UNORM_S8_UINT words (u32, depth in the low 24 bits)
     int W, H;               // full-frame size
     int depth_row0;         // global row of depth[0]
     int row0, row1;         // global L0 rows to process; row0 % 16 == 0
@@ -27,7 +28,7 @@ struct PrepareArgs {
     float zbx, zby;         // ZBufferParams.xy (AmbientOcclusion.cs:561-568)
     int raw;                // 1: Linearize (DS1:37-48); 0: depth is already linear
     int reversed_z;         // UNITY_REVERSED_Z (DS1:41-45)
-    int vec_ok;             // depth pointer 16B aligned and W % 4 == 0
+    int vec_ok;             // depth pointer 16B aligned and rows stay 16B aligned (W % 4 == 0 for f32/u32, W % 8 == 0 for u16)
 };
 cudaError_t launch_prepare_depth(const PrepareArgs &a, cudaStream_t s);
 
@@ -77,6 +78,9 @@ constexpr int kUpsAoBoxW = 64, kUpsAoBoxH = 22;
 // ---- debug: synthesise a TiledDepth<k> view (reference layout [16][sh][sw], f16 bits) ----------
 cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int sw, int sh, float pad,
                                __half *out, cudaStream_t s);
+
+// ---- composite (Blit.shader passes 1 and 2): colour *= ao, 4 pixels per thread ------------------------
+cudaError_t launch_composite(const uint8_t *ao, void *color, long long npix, int half, int rgb, int alpha, int one_minus, cudaStream_t s);
 
 // ---- self test: div_fast / rcp_fast vs the IEEE operators on n random in-range operand pairs ------
 cudaError_t launch_selftest_div(uint64_t n, uint32_t seed, unsigned long long *mismatch_dev, cudaStream_t s);

@@ -353,16 +353,17 @@ int ensure_ready(MeaoCtx *c)
 int record_downsample(MeaoCtx *c, const void *depth, int kind, cudaStream_t s)
 {
     PrepareArgs a{};
-    a.depth = (const float *)depth;
+    a.depth = depth;
+    a.in_format = (kind == MEAO_DEPTH_RAW_D16_UNORM) ? 1 : (kind == MEAO_DEPTH_RAW_D24S8 ? 2 : 0);
     a.W = c->W; a.H = c->H;
     a.depth_row0 = c->band0;
     a.row0 = c->band0; a.row1 = c->band1;
     a.lin = c->lin; a.lin_pitch = c->lin_pitch;
     for (int k = 1; k <= 4; k++) { a.low[k - 1] = c->low[k]; a.low_pitch[k - 1] = c->low_pitch[k]; }
     a.zbx = c->plan.zb[0]; a.zby = c->plan.zb[1];
-    a.raw = (kind == MEAO_DEPTH_RAW_F32);
+    a.raw = (kind != MEAO_DEPTH_LINEAR_F32);
     a.reversed_z = c->camera.reversed_z;
-    a.vec_ok = (((uintptr_t)depth & 15) == 0) && (c->W % 4 == 0);
+    a.vec_ok = (((uintptr_t)depth & 15) == 0) && (c->W % (a.in_format == 1 ? 8 : 4) == 0);
     c->last_kind = kind;
     CUDA_TRY(c, launch_prepare_depth(a, s));
     c->launches++;
@@ -377,7 +378,7 @@ int record_render(MeaoCtx *c, int k, int kind, cudaStream_t s)
     a.low = c->low[k]; a.lw = c->lw[k]; a.lh = c->lh[k]; a.lpitch = c->low_pitch[k];
     a.occ = c->occ[k]; a.opitch = c->occ_pitch[k];
     a.sw = c->lw[k + 2]; a.sh = c->lh[k + 2];
-    a.pad = host_f16_round((kind == MEAO_DEPTH_RAW_F32) ? c->plan.pad[k] : 0.0f);
+    a.pad = host_f16_round((kind != MEAO_DEPTH_LINEAR_F32) ? c->plan.pad[k] : 0.0f);
     for (int i = 0; i < 7; i++) {
         a.inv_thickness[i] = c->plan.inv_thickness[k][idx[i]];
         a.neg_front[i] = -(a.inv_thickness[i] - 0.5f);                                               // Render.compute:85
@@ -826,7 +827,7 @@ int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void 
 {
     int rc = ensure_ready(c); if (rc) return rc;
     if (!depth || !ao_out) return fail(c, MEAO_ERR_INVALID, "depth / ao_out is NULL");
-    if (kind != MEAO_DEPTH_RAW_F32 && kind != MEAO_DEPTH_LINEAR_F32) return fail(c, MEAO_ERR_INVALID, "bad depth kind %d", kind);
+    if (kind < MEAO_DEPTH_RAW_F32 || kind > MEAO_DEPTH_RAW_D24S8) return fail(c, MEAO_ERR_INVALID, "bad depth kind %d", kind);
     if (c->need_low[1].lo < c->own_low[1].lo || c->need_low[1].hi > c->own_low[1].hi)
         return fail(c, MEAO_ERR_INVALID, "interior row band: use meao_render_band_prepare / halo exchange / meao_render_band_finish");
     cudaStream_t s = (cudaStream_t)stream;
@@ -858,14 +859,15 @@ int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void 
     return MEAO_OK;
 }
 
-int meao_render_host_async(MeaoCtx *c, const float *depth_host, int32_t kind, uint8_t *ao_host, int32_t slot)
+int meao_render_host_async(MeaoCtx *c, const void *depth_host, int32_t kind, uint8_t *ao_host, int32_t slot)
 {
     int rc = ensure_ready(c); if (rc) return rc;
     if (!depth_host || !ao_host) return fail(c, MEAO_ERR_INVALID, "depth / ao_out is NULL");
     if (slot != 0 && slot != 1) return fail(c, MEAO_ERR_INVALID, "slot must be 0 or 1");
     const size_t rows = (size_t)(c->band1 - c->band0);
     cudaStream_t s = c->slot_stream[slot];
-    CUDA_TRY(c, cudaMemcpyAsync(c->depth_stage[slot], depth_host, rows * c->W * sizeof(float), cudaMemcpyHostToDevice, s));
+    const size_t esz = (kind == MEAO_DEPTH_RAW_D16_UNORM) ? 2 : 4;
+    CUDA_TRY(c, cudaMemcpyAsync(c->depth_stage[slot], depth_host, rows * c->W * esz, cudaMemcpyHostToDevice, s));
     // the two slots share the context's intermediates: kernels of consecutive frames are serialised, copies are not
     if (c->compute_done_valid) CUDA_TRY(c, cudaStreamWaitEvent(s, c->compute_done, 0));
     if ((rc = meao_render(c, c->depth_stage[slot], kind, c->ao_stage[slot], s))) return rc;
@@ -885,7 +887,7 @@ int meao_host_wait(MeaoCtx *c, int32_t slot)
     return MEAO_OK;
 }
 
-int meao_render_host(MeaoCtx *c, const float *depth_host, int32_t kind, uint8_t *ao_host)
+int meao_render_host(MeaoCtx *c, const void *depth_host, int32_t kind, uint8_t *ao_host)
 {
     int rc = meao_render_host_async(c, depth_host, kind, ao_host, 0);
     if (rc) return rc;
@@ -952,7 +954,7 @@ int meao_get_buffer(MeaoCtx *c, int32_t id, void *host_out, size_t host_bytes)
         const int k = id - 5;
         __half *tmp = nullptr;
         CUDA_TRY(c, cudaMalloc(&tmp, need));
-        const float pad = host_f16_round((c->last_kind == MEAO_DEPTH_RAW_F32) ? c->plan.pad[k] : 0.0f);
+        const float pad = host_f16_round((c->last_kind != MEAO_DEPTH_LINEAR_F32) ? c->plan.pad[k] : 0.0f);
         cudaError_t e = launch_synth_tiled(c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], c->lw[k + 2], c->lh[k + 2], pad, tmp, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, tmp, need, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -1024,6 +1026,35 @@ int meao_zbuffer_params(MeaoCtx *c, float out[4])
 {
     if (plan_only(c) || !out) return MEAO_ERR_INVALID;
     memcpy(out, c->plan.zb, 16);
+    return MEAO_OK;
+}
+
+static int composite_args(MeaoCtx *c, const void *ao, const void *color, int fmt)
+{
+    if (!ao || !color) return fail(c, MEAO_ERR_INVALID, "ao / colour target is NULL");
+    if (fmt != MEAO_FMT_RGBA8_UNORM && fmt != MEAO_FMT_RGBA16_FLOAT) return fail(c, MEAO_ERR_INVALID, "bad colour format %d", fmt);
+    if (((uintptr_t)ao & 3) || ((uintptr_t)color & 15)) return fail(c, MEAO_ERR_INVALID, "composite needs a 4-byte aligned AO and a 16-byte aligned colour pointer");
+    return 0;
+}
+
+int meao_composite_framebuffer(MeaoCtx *c, const void *ao, void *color, int32_t fmt, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if ((rc = composite_args(c, ao, color, fmt))) return rc;
+    const long long npix = (long long)c->W * (c->band1 - c->band0);
+    CUDA_TRY(c, launch_composite((const uint8_t *)ao, color, npix, fmt == MEAO_FMT_RGBA16_FLOAT, 1, 1, 0, (cudaStream_t)stream));
+    c->launches++;
+    return MEAO_OK;
+}
+
+int meao_composite_gbuffer(MeaoCtx *c, const void *ao, void *g0, void *g3, int32_t fmt3, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if ((rc = composite_args(c, ao, g0, MEAO_FMT_RGBA8_UNORM)) || (rc = composite_args(c, ao, g3, fmt3))) return rc;
+    const long long npix = (long long)c->W * (c->band1 - c->band0);
+    CUDA_TRY(c, launch_composite((const uint8_t *)ao, g0, npix, 0, 0, 1, 1, (cudaStream_t)stream));                               // gbuffer0.a
+    CUDA_TRY(c, launch_composite((const uint8_t *)ao, g3, npix, fmt3 == MEAO_FMT_RGBA16_FLOAT, 1, 0, 1, (cudaStream_t)stream));   // gbuffer3.rgb
+    c->launches += 2;
     return MEAO_OK;
 }
 

@@ -30,7 +30,52 @@ __device__ __forceinline__ float linearize(float depth, float zbx, float zby)
     return dist;
 }
 
-template <bool RAW, bool REVERSED>
+// native depth formats: the camera depth texture read by Blit.shader pass 0 (:48-64) is a D32_FLOAT,
+// D24_UNORM_S8_UINT or D16_UNORM resource; SAMPLE_DEPTH_TEXTURE returns code / (2^n - 1) for the UNORM ones
+// (D3D UNORM -> FLOAT rule: (float)code * (1.0f / (2^n - 1))).
+enum { IN_F32 = 0, IN_D16 = 1, IN_D24S8 = 2 };
+
+template <int IN>
+__device__ __forceinline__ void load8(const void *base, size_t elem_index, bool full, int valid, float (&v)[8])
+{
+    if (IN == IN_F32) {
+        const float *src = reinterpret_cast<const float *>(base) + elem_index;
+        if (full) {
+            const float4 q0 = ldg_stream_f4(src), q1 = ldg_stream_f4(src + 4);
+            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = (e < valid) ? __ldg(src + e) : 0.0f;
+        }
+    } else if (IN == IN_D16) {
+        const uint16_t *src = reinterpret_cast<const uint16_t *>(base) + elem_index;
+        uint32_t c[8];
+        if (full) {
+            const uint4 q = ldg_stream_u4(src);
+            c[0] = q.x & 0xffffu; c[1] = q.x >> 16; c[2] = q.y & 0xffffu; c[3] = q.y >> 16;
+            c[4] = q.z & 0xffffu; c[5] = q.z >> 16; c[6] = q.w & 0xffffu; c[7] = q.w >> 16;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) c[e] = (e < valid) ? __ldg(src + e) : 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = __fmul_rn((float)c[e], 1.0f / 65535.0f);
+    } else {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(base) + elem_index;
+        uint32_t c[8];
+        if (full) {
+            const uint4 q0 = ldg_stream_u4(src), q1 = ldg_stream_u4(src + 4);
+            c[0] = q0.x; c[1] = q0.y; c[2] = q0.z; c[3] = q0.w; c[4] = q1.x; c[5] = q1.y; c[6] = q1.z; c[7] = q1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) c[e] = (e < valid) ? __ldg(src + e) : 0u;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = __fmul_rn((float)(c[e] & 0xffffffu), 1.0f / 16777215.0f);   // depth = low 24 bits, stencil = high 8
+    }
+}
+
+template <bool RAW, bool REVERSED, int IN>
 __global__ void __launch_bounds__(kPrepThreads) prepare_depth_kernel(const PrepareArgs a)
 {
 #ifdef MEAO_DEVICE_OK
@@ -46,17 +91,7 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_depth_kernel(const Prepa
     for (int p = 0; p < 2; p++) {
         const int y = ybase + warp + 8 * p;
         rowok[p] = y < a.row1;
-        if (rowok[p]) {
-            const float *src = a.depth + (size_t)(y - a.depth_row0) * a.W + x;
-            if (full) {
-                float4 q0 = ldg_stream_f4(src), q1 = ldg_stream_f4(src + 4);
-                v[p][0] = q0.x; v[p][1] = q0.y; v[p][2] = q0.z; v[p][3] = q0.w;
-                v[p][4] = q1.x; v[p][5] = q1.y; v[p][6] = q1.z; v[p][7] = q1.w;
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; e++) v[p][e] = (x + e < a.W) ? __ldg(src + e) : 0.0f;
-            }
-        }
+        if (rowok[p]) load8<IN>(a.depth, (size_t)(y - a.depth_row0) * a.W + x, full, a.W - x, v[p]);
     }
 
 #pragma unroll
@@ -112,11 +147,17 @@ cudaError_t launch_prepare_depth(const PrepareArgs &a, cudaStream_t s)
 {
     if (a.row1 <= a.row0) return cudaSuccess;
     dim3 grid(ceil_div(a.W, kPrepTileW), ceil_div(a.row1 - a.row0, kPrepTileH));
-    if (a.raw) {
-        if (a.reversed_z) prepare_depth_kernel<true, true><<<grid, kPrepThreads, 0, s>>>(a);
-        else              prepare_depth_kernel<true, false><<<grid, kPrepThreads, 0, s>>>(a);
+    if (!a.raw) {
+        prepare_depth_kernel<false, true, IN_F32><<<grid, kPrepThreads, 0, s>>>(a);
+    } else if (a.in_format == IN_D16) {
+        if (a.reversed_z) prepare_depth_kernel<true, true, IN_D16><<<grid, kPrepThreads, 0, s>>>(a);
+        else              prepare_depth_kernel<true, false, IN_D16><<<grid, kPrepThreads, 0, s>>>(a);
+    } else if (a.in_format == IN_D24S8) {
+        if (a.reversed_z) prepare_depth_kernel<true, true, IN_D24S8><<<grid, kPrepThreads, 0, s>>>(a);
+        else              prepare_depth_kernel<true, false, IN_D24S8><<<grid, kPrepThreads, 0, s>>>(a);
     } else {
-        prepare_depth_kernel<false, true><<<grid, kPrepThreads, 0, s>>>(a);
+        if (a.reversed_z) prepare_depth_kernel<true, true, IN_F32><<<grid, kPrepThreads, 0, s>>>(a);
+        else              prepare_depth_kernel<true, false, IN_F32><<<grid, kPrepThreads, 0, s>>>(a);
     }
     return cudaGetLastError();
 }

@@ -615,3 +615,42 @@ void meao_oracle_run(MeaoOracle *o, const float *depth, int threads)
     for (int k = 1; k <= 4; k++) meao_oracle_render(o, k, threads);
     for (int lo = 4; lo >= 1; lo--) meao_oracle_upsample(o, lo, threads);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Composite (Blit.shader passes 1 and 2; AmbientOcclusion.cs:822-839)
+ * ---------------------------------------------------------------------------------------- */
+static void scale_px(void *rgba, int is_half, size_t i, float f, int rgb, int alpha)
+{
+    for (int ch = 0; ch < 4; ch++) {
+        if (!((ch < 3) ? rgb : alpha)) continue;                    /* blend factor 1: destination unchanged */
+        if (is_half) {
+            uint16_t *p = (uint16_t *)rgba + i * 4 + ch;
+            *p = meao_oracle_f32_to_f16_bits(meao_oracle_f16_bits_to_f32(*p) * f);
+        } else {
+            uint8_t *p = (uint8_t *)rgba + i * 4 + ch;
+            *p = meao_oracle_unorm8_code(((float)*p * (1.0f / 255.0f)) * f);
+        }
+    }
+}
+
+/* pass 2: return tex2D(_AOTexture, uv).r  with  Blend Zero SrcAlpha  (Blit.shader:86,96-99) */
+void meao_oracle_composite_framebuffer(const uint8_t *ao_codes, void *rgba, int is_half, size_t npix)
+{
+    for (size_t i = 0; i < npix; i++) {
+        float t = (float)ao_codes[i] * (1.0f / 255.0f);
+        scale_px(rgba, is_half, i, t, 1, 1);
+    }
+}
+
+/* pass 1: ao = 1 - tex.r; gbuffer0 = (0,0,0,ao), gbuffer3 = (ao,ao,ao,0) with
+ * Blend Zero OneMinusSrcColor, Zero OneMinusSrcAlpha  (Blit.shader:68,83-89) */
+void meao_oracle_composite_gbuffer(const uint8_t *ao_codes, uint8_t *gbuffer0_rgba8, void *gbuffer3_rgba, int g3_is_half, size_t npix)
+{
+    for (size_t i = 0; i < npix; i++) {
+        float t = (float)ao_codes[i] * (1.0f / 255.0f);
+        volatile float ao = 1.0f - t;                               /* Blit.shader:83 */
+        float f = 1.0f - ao;                                        /* OneMinusSrc* */
+        scale_px(gbuffer0_rgba8, 0, i, f, 0, 1);
+        scale_px(gbuffer3_rgba, g3_is_half, i, f, 1, 0);
+    }
+}

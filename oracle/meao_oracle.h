@@ -38,6 +38,7 @@
 #ifndef MEAO_ORACLE_H
 #define MEAO_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -103,6 +104,13 @@ void meao_oracle_downsample(MeaoOracle *o, const float *depth, int threads);   /
 void meao_oracle_render(MeaoOracle *o, int level /*1..4*/, int threads);       /* REN main_interleaved */
 void meao_oracle_upsample(MeaoOracle *o, int lo_level /*4..1*/, int threads);  /* UPS main(_blendout) */
 void meao_oracle_run(MeaoOracle *o, const float *depth, int threads);          /* steps 1..10 */
+
+/* Composite passes.  Fixed-function output-merger blending restated in fp32:
+ *   pass 2, Blit.shader:84-101 + "Blend Zero SrcAlpha"                          : dst.rgba *= ao
+ *   pass 1, Blit.shader:66-92 + "Blend Zero OneMinusSrcColor, Zero OneMinusSrcAlpha": gbuffer0.a *= 1-(1-ao), gbuffer3.rgb *= 1-(1-ao)
+ * ao = code * (1/255); RGBA8 targets load code*(1/255) and store through the UNORM8 rule; RGBA16F load exact, store RTNE. */
+void meao_oracle_composite_framebuffer(const uint8_t *ao_codes, void *rgba, int is_half, size_t npix);
+void meao_oracle_composite_gbuffer(const uint8_t *ao_codes, uint8_t *gbuffer0_rgba8, void *gbuffer3_rgba, int g3_is_half, size_t npix);
 
 /* debug ids 1..17 (AO.cs:787-808).  Returns pointer + dims (depth = 16 for tiled). */
 const float *meao_oracle_get_buffer(const MeaoOracle *o, int debug_id, int *w, int *h, int *slices);

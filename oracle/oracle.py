@@ -78,6 +78,8 @@ def _lib(variant: str = "fma") -> C.CDLL:
         lib.meao_oracle_sample_thickness.argtypes = [fp]
         lib.meao_oracle_render_constants.argtypes = [C.POINTER(_OracleStruct), C.c_int, fp, fp, fp, fp, fp]
         lib.meao_oracle_upsample_constants.argtypes = [C.POINTER(_OracleStruct), C.c_int, fp, fp, fp, fp, fp, fp]
+        lib.meao_oracle_composite_framebuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
+        lib.meao_oracle_composite_gbuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
         _libs[variant] = lib
     return _libs[variant]
 
@@ -216,3 +218,22 @@ class Oracle:
 
     def unorm8_code(self, x: float) -> int:
         return self._lib.meao_oracle_unorm8_code(C.c_float(x))
+
+
+def composite_framebuffer(ao_codes: np.ndarray, color: np.ndarray) -> np.ndarray:
+    """Blit.shader pass 2: color (uint8 [...,4] RGBA8 or float16 [...,4] RGBA16F) *= ao.  Returns a new array."""
+    ao = np.ascontiguousarray(ao_codes, np.uint8)
+    out = np.ascontiguousarray(color).copy()
+    assert out.dtype in (np.uint8, np.float16) and out.shape[-1] == 4 and out.size == ao.size * 4
+    _lib().meao_oracle_composite_framebuffer(ao.ctypes.data, out.ctypes.data, int(out.dtype == np.float16), ao.size)
+    return out
+
+
+def composite_gbuffer(ao_codes: np.ndarray, gbuffer0: np.ndarray, gbuffer3: np.ndarray):
+    """Blit.shader pass 1: gbuffer0 (RGBA8).a and gbuffer3 (RGBA8 / RGBA16F).rgb *= 1-(1-ao).  Returns new arrays."""
+    ao = np.ascontiguousarray(ao_codes, np.uint8)
+    g0 = np.ascontiguousarray(gbuffer0).copy()
+    g3 = np.ascontiguousarray(gbuffer3).copy()
+    assert g0.dtype == np.uint8 and g3.dtype in (np.uint8, np.float16)
+    _lib().meao_oracle_composite_gbuffer(ao.ctypes.data, g0.ctypes.data, g3.ctypes.data, int(g3.dtype == np.float16), ao.size)
+    return g0, g3

@@ -1,0 +1,6 @@
+#!/bin/bash
+# compute-sanitizer over one small frame + one banded frame (run on the GPU box); summary lines only
+for tool in memcheck racecheck initcheck synccheck; do
+  echo "== $tool"
+  compute-sanitizer --tool $tool --print-limit 5 python scripts/debug_parity.py 330 170 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|final mismatches|Error|hazard" | head -8
+done

@@ -219,3 +219,19 @@ def test_oracle_reproduces_golden_fixture(path):
                 assert np.array_equal(o.buffer(bid).astype(np.float16).view(np.uint16), ref.view(np.uint16)), bid
         else:
             assert np.array_equal(o.buffer(bid), ref), bid
+
+
+def test_composite_oracle_identities():
+    """ao = 255 leaves every target unchanged (x * 1); ao = 0 zeroes the scaled channels; untouched channels survive."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(1)
+    c8 = rng.integers(0, 256, size=(7, 9, 4), dtype=np.uint8)
+    c16 = rng.uniform(0, 8, size=(7, 9, 4)).astype(np.float16)
+    one, zero = np.full((7, 9), 255, np.uint8), np.zeros((7, 9), np.uint8)
+    assert np.array_equal(O.composite_framebuffer(one, c8), c8) and np.array_equal(O.composite_framebuffer(one, c16), c16)
+    assert not O.composite_framebuffer(zero, c8).any() and not O.composite_framebuffer(zero, c16).any()
+    g0, g3 = O.composite_gbuffer(zero, c8, c16)
+    assert np.array_equal(g0[..., :3], c8[..., :3]) and not g0[..., 3].any()
+    assert np.array_equal(g3[..., 3], c16[..., 3]) and not g3[..., :3].any()
+    g0, g3 = O.composite_gbuffer(one, c8, c8)
+    assert np.array_equal(g0, c8) and np.array_equal(g3, c8)

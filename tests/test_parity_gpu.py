@@ -399,3 +399,59 @@ def test_graph_cached_band_phases_equal_whole_frame(torch_cuda, W, H, bands):
         torch.cuda.synchronize()
         got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
         assert int((got != ref).sum()) == 0
+
+
+@pytest.mark.parametrize("W,H", [(640, 360), (321, 203)])
+def test_composite_passes_bit_exact(torch_cuda, W, H):
+    """Blit.shader pass 2 (frame buffer *= ao) and pass 1 (G-buffer occlusion / ambient *= 1-(1-ao))
+    on RGBA8 and RGBA16F targets, against the oracle's fp32 restatement of the output-merger blend."""
+    from miniengineao_b200 import synth
+    from oracle import oracle as O
+    torch = torch_cuda
+    ao, orc = _mk(W, H, intensity=1.1)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=3))
+    ref_ao = orc.run(depth)
+    ao_dev = ao.render(torch.from_numpy(depth).cuda())
+    rng = np.random.default_rng(0)
+    c8 = rng.integers(0, 256, size=(H, W, 4), dtype=np.uint8)
+    c16 = (rng.uniform(0, 4, size=(H, W, 4)) ** 3).astype(np.float16)
+    for host in (c8, c16):
+        dev = torch.from_numpy(host.copy()).cuda()
+        ao.composite_framebuffer(ao_dev, dev)
+        torch.cuda.synchronize()
+        exp = O.composite_framebuffer(ref_ao, host)
+        assert np.array_equal(dev.cpu().numpy().view(np.uint8), exp.view(np.uint8)), host.dtype
+    for g3 in (c8, c16):
+        g0d, g3d = torch.from_numpy(c8.copy()).cuda(), torch.from_numpy(g3.copy()).cuda()
+        ao.composite_gbuffer(ao_dev, g0d, g3d)
+        torch.cuda.synchronize()
+        e0, e3 = O.composite_gbuffer(ref_ao, c8, g3)
+        assert np.array_equal(g0d.cpu().numpy(), e0)
+        assert np.array_equal(g3d.cpu().numpy().view(np.uint8), e3.view(np.uint8)), g3.dtype
+
+
+@pytest.mark.parametrize("W,H", [(640, 360), (250, 131)])
+def test_native_depth_formats(torch_cuda, W, H):
+    """D16_UNORM and D24_UNORM_S8_UINT ingest (what Blit.shader pass 0 samples).  The oracle sees
+    the float the D3D UNORM->FLOAT rule produces, code * (1 / (2^n - 1))."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    lin = synth.random_depth(W, H, seed=17)
+    raw = synth.lin01_to_raw(lin).astype(np.float64)
+    for bits, dt in ((16, np.uint16), (24, np.uint32)):
+        ao, orc = _mk(W, H, intensity=1.1)
+        full = (1 << bits) - 1
+        codes = np.clip(np.rint(raw * full), 1, full).astype(np.uint32)          # no sky codes
+        as_float = (codes.astype(np.float32) * np.float32(1.0 / full)).astype(np.float32)
+        ref = orc.run(as_float)
+        if bits == 16:
+            dev = torch.from_numpy(codes.astype(np.uint16).view(np.int16)).cuda().view(torch.uint16)
+            host = codes.astype(np.uint16)
+        else:
+            words = codes | (np.uint32(0xA5) << np.uint32(24))                    # stencil bits must be ignored
+            dev = torch.from_numpy(words.view(np.int32)).cuda()
+            host = words
+        got = ao.render(dev).cpu().numpy()
+        assert np.array_equal(got, ref), bits
+        _compare_all(ao, orc, f"D{bits}")
+        assert np.array_equal(ao.render_host(host), ref), bits
