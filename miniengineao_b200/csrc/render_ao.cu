@@ -194,12 +194,6 @@ cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const Ren
     const int ybase = a.row0 & ~3;
     dim3 grid(ceil_div(a.lw, kTW), ceil_div(a.row1 - ybase, kTH));
     const size_t smem = (size_t)kSW * kSH * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(render_ao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     render_ao_kernel<<<grid, kThreads, smem, s>>>(low_map, a, use_tma ? 1 : 0);
     return cudaGetLastError();
 }

@@ -455,3 +455,18 @@ def test_native_depth_formats(torch_cuda, W, H):
         assert np.array_equal(got, ref), bits
         _compare_all(ao, orc, f"D{bits}")
         assert np.array_equal(ao.render_host(host), ref), bits
+
+
+def test_pure_c_client_renders_golden_frame(torch_cuda, tmp_path):
+    """The drop-in boundary from plain C: tests/c_abi/smoke.c renders a committed golden fixture through
+    meao_render_host and must reproduce its AO bytes."""
+    import os, subprocess
+    from test_abi import _build_c_client
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corridor_160x90.npz"))
+    H, W = g["depth"].shape
+    dpath, apath = os.path.join(str(tmp_path), "depth.f32"), os.path.join(str(tmp_path), "ao.u8")
+    g["depth"].astype(np.float32).tofile(dpath)
+    g["ao"].astype(np.uint8).tofile(apath)
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe, "render", str(W), str(H), dpath, apath, repr(float(g["params"][4]))], capture_output=True, text=True)
+    assert r.returncode == 0 and " 0 mismatching pixels" in r.stdout, r.stdout + r.stderr
