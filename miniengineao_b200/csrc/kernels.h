@@ -48,7 +48,10 @@ struct RenderArgs {
     int row0, row1;         // output rows (level k) to produce
 };
 cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const RenderArgs &a, cudaStream_t s);
-constexpr int kRenderBoxW = 96, kRenderBoxH = 48;     // TMA box of the render kernel (f32 elements)
+#ifndef MEAO_REN_TH
+#define MEAO_REN_TH 32
+#endif
+constexpr int kRenderBoxW = 96, kRenderBoxH = MEAO_REN_TH + 32;     // TMA box of the render kernel (f32 elements)
 
 // ---- stage 3: blur_upsample = Upsample.compute main / main_blendout, one level ----------------
 struct UpsampleArgs {
