@@ -56,8 +56,21 @@ __device__ __forceinline__ float2 pair_eval2(float2 S1, float2 S2, float2 inv_ra
     const float2 d2 = __ffma2_rn(S2, inv_range, neg_front);             // REN:66
     const float p1x = __saturatef(__fmul_rn(rf, d1.x)), p1y = __saturatef(__fmul_rn(rf, d1.y));   // REN:68
     const float p2x = __saturatef(__fmul_rn(rf, d2.x)), p2y = __saturatef(__fmul_rn(rf, d2.y));   // REN:69
+    // clamp(d, p, 1): either max(saturate(d), p) (FADD.SAT on the FMA pipe + FMNMX) or the literal
+    // min(max(d, p), 1) (two FMNMX on the ALU pipe); both are exact, the mix balances the two pipes
+#ifndef MEAO_REN_CLAMP_MODE
+#define MEAO_REN_CLAMP_MODE 1
+#endif
+#if MEAO_REN_CLAMP_MODE == 0
     const float2 c1 = make_float2(fmaxf(__saturatef(d1.x), p2x), fmaxf(__saturatef(d1.y), p2y));
     const float2 c2 = make_float2(fmaxf(__saturatef(d2.x), p1x), fmaxf(__saturatef(d2.y), p1y));
+#elif MEAO_REN_CLAMP_MODE == 1
+    const float2 c1 = make_float2(fmaxf(__saturatef(d1.x), p2x), fmaxf(__saturatef(d1.y), p2y));
+    const float2 c2 = make_float2(fminf(fmaxf(d2.x, p1x), 1.0f), fminf(fmaxf(d2.y, p1y), 1.0f));
+#else
+    const float2 c1 = make_float2(fminf(fmaxf(d1.x, p2x), 1.0f), fminf(fmaxf(d1.y, p2y), 1.0f));
+    const float2 c2 = make_float2(fminf(fmaxf(d2.x, p1x), 1.0f), fminf(fmaxf(d2.y, p1y), 1.0f));
+#endif
     const float2 sum = __fadd2_rn(c1, c2);
     return make_float2(__saturatef(fmaf(-p1x, p2x, sum.x)), __saturatef(fmaf(-p1y, p2y, sum.y)));   // REN:71-74
 }

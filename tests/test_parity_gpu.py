@@ -470,3 +470,24 @@ def test_pure_c_client_renders_golden_frame(torch_cuda, tmp_path):
     exe = _build_c_client(tmp_path)
     r = subprocess.run([exe, "render", str(W), str(H), dpath, apath, repr(float(g["params"][4]))], capture_output=True, text=True)
     assert r.returncode == 0 and " 0 mismatching pixels" in r.stdout, r.stdout + r.stderr
+
+
+def test_random_configurations_bit_exact(torch_cuda):
+    """32 seeded random (size, parameter, camera) configurations, full pipe + every intermediate buffer."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    rng = np.random.default_rng(20260923)
+    for i in range(32):
+        W, H = int(rng.integers(1, 420)), int(rng.integers(1, 300))
+        params = dict(intensity=float(rng.uniform(0, 2)), thickness_modifier=float(rng.uniform(1, 10)),
+                      blur_tolerance=float(rng.uniform(-8, -1)), upsample_tolerance=float(rng.uniform(-12, -1)),
+                      noise_filter_tolerance=float(rng.uniform(-8, 0)), reversed_z=bool(rng.integers(0, 2)))
+        ao, orc = _mk(W, H, **params)
+        depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=int(rng.integers(0, 1 << 30))), reversed_z=params["reversed_z"])
+        if i % 4 == 0 and W > 8 and H > 8:
+            depth[H // 3: H // 3 + 3, W // 4: W // 4 + 5] = 0.0 if params["reversed_z"] else 1.0      # a patch of sky
+        ref = orc.run(depth)
+        got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+        assert np.array_equal(got, ref), (i, W, H, params)
+        _compare_all(ao, orc, f"cfg {i}: {W}x{H} {params}")
+        ao.close()
