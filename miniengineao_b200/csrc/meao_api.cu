@@ -199,6 +199,8 @@ void build_plan(MeaoCtx *c)
 
 void drop_graph(MeaoCtx *c)
 {
+    if (c->graphs.empty()) return;
+    cudaDeviceSynchronize();            // a re-plan is rare; never destroy an executable graph that may still be in flight
     for (auto &kv : c->graphs) cudaGraphExecDestroy(kv.second);
     c->graphs.clear();
 }
