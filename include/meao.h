@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define MEAO_ABI_VERSION 1
+#define MEAO_ABI_VERSION 2   /* 2: + MeaoVariants, meao_stage_render_wide, meao_debug_view, buffer ids 18..21 */
 
 typedef struct MeaoCtx MeaoCtx;
 
@@ -89,13 +89,30 @@ typedef enum {
     MEAO_BUF_OCCLUSION1 = 10, MEAO_BUF_OCCLUSION2 = 11,         /* L1..L4, unorm8 */
     MEAO_BUF_OCCLUSION3 = 12, MEAO_BUF_OCCLUSION4 = 13,
     MEAO_BUF_COMBINED1 = 14, MEAO_BUF_COMBINED2 = 15, MEAO_BUF_COMBINED3 = 16,   /* L1..L3, unorm8 */
-    MEAO_BUF_AMBIENT_OCCLUSION = 17                             /* L0, unorm8 */
+    MEAO_BUF_AMBIENT_OCCLUSION = 17,                            /* L0, unorm8 */
+    /* extension ids (not in AO.cs:787-808): output of Render.compute kernel "main" (MeaoVariants.high_quality_mask) */
+    MEAO_BUF_HIGH_QUALITY1 = 18, MEAO_BUF_HIGH_QUALITY2 = 19,   /* L1..L4, unorm8 */
+    MEAO_BUF_HIGH_QUALITY3 = 20, MEAO_BUF_HIGH_QUALITY4 = 21
 } MeaoBufferId;
 
 typedef struct {
     int32_t width, height, slices;  /* reference texture dimensions (AO.cs:276-281; slices = 16 when tiled, AO.cs:154) */
     int32_t elem_bytes;             /* 1 = unorm8, 2 = f16 bits, 4 = f32  (AO.cs:262-273) */
 } MeaoBufferDesc;
+
+/* Shader / host variants that the reference SHIPS but never selects.  All zero = exactly what
+ * AmbientOcclusion.cs records; every field is a plan input like MeaoParams (a change re-plans, AO.cs:334-347). */
+typedef struct {
+    int32_t single_pass_stereo;   /* singlePassStereoEnabled (AO.cs:392-401): ThicknessMultiplier *= 2 (AO.cs:680).  The caller passes the
+                                     DOUBLE-WIDE eye pair to meao_resize, as LateUpdate / RebuildCommandBuffers do (AO.cs:338-341, 501-504). */
+    int32_t sample_exhaustively;  /* Render.compute:144-159 "#define SAMPLE_EXHAUSTIVELY": 68 taps instead of the 36-tap checker, and the
+                                     weight zeroing of AO.cs:709-715 ("FIXME: should we support SAMPLE_EXHAUSTIVELY mode?") is skipped */
+    int32_t high_quality_mask;    /* bit k-1 (k = 1..4): level k ALSO runs Render.compute kernel "main" (WIDE_SAMPLING, :22,27-29,46-50,79-82:
+                                     non-tiled source LowDepth<k>, so PushRenderCommands takes the "!source.isTiled" branch AO.cs:679) into
+                                     HighQuality<k>, and the upsample whose LOW level is k runs Upsample.compute kernel "main_premin" /
+                                     "main_premin_blendout" (:23,25,32-34,58-60) with LoResAO2 = HighQuality<k>.  E.g. 8 = coarsest level
+                                     only, 15 = every level (the quality ladder of the upstream MiniEngine sample, which is not vendored). */
+} MeaoVariants;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
 /* replaces: component construction + DoLazyInitialization (AO.cs:440-494). */
@@ -111,6 +128,9 @@ int meao_abi_version(void);
 int meao_set_params(MeaoCtx *ctx, const MeaoParams *params);
 int meao_get_params(const MeaoCtx *ctx, MeaoParams *out);
 void meao_default_params(MeaoParams *out);          /* AO.cs:20-68 defaults */
+/* Selects the undispatched shader variants above; returns 1 if the plan was dirtied, 0 if not. */
+int meao_set_variants(MeaoCtx *ctx, const MeaoVariants *variants);
+int meao_get_variants(const MeaoCtx *ctx, MeaoVariants *out);
 /* replaces: CalculateZBufferParams / CalculateTanHalfFovHeight inputs (AO.cs:561-573). */
 int meao_set_camera(MeaoCtx *ctx, const MeaoCamera *camera);
 /* replaces: RTHandle.SetBaseDimensions + AllocateNow + the rebuild it triggers (AO.cs:338-341, 501-506).
@@ -143,8 +163,12 @@ void meao_host_free(void *p);
 int meao_stage_downsample(MeaoCtx *ctx, const void *depth_dev, int32_t depth_kind, void *stream);
 /* replaces: PushRenderCommands (AO.cs:660-748) for TiledDepth<level> -> Occlusion<level>, level 1..4 */
 int meao_stage_render(MeaoCtx *ctx, int32_t level, void *stream);
+/* PushRenderCommands (AO.cs:660-748) for a NON-tiled source: LowDepth<level> -> HighQuality<level> with Render.compute kernel
+ * "main" (FindKernel would name it instead of "main_interleaved", AO.cs:728; thread-group size 16x16 from AO.cs:739-747). */
+int meao_stage_render_wide(MeaoCtx *ctx, int32_t level, void *stream);
 /* replaces: PushUpsampleCommands (AO.cs:750-785) with the wiring of AO.cs:528-531; lo_level 4..1.
- * lo_level == 1 writes the final AO into ao_out_dev (or the context's own result buffer if NULL). */
+ * lo_level == 1 writes the final AO into ao_out_dev (or the context's own result buffer if NULL).
+ * Uses the main_premin variants for the levels selected in MeaoVariants.high_quality_mask. */
 int meao_stage_upsample(MeaoCtx *ctx, int32_t lo_level, void *ao_out_dev, void *stream);
 
 /* ---- buffers (debug views, AO.cs:787-820) ------------------------------------------------------ */
@@ -154,13 +178,21 @@ int meao_buffer_desc(const MeaoCtx *ctx, int32_t buffer_id, MeaoBufferDesc *out)
  * The TiledDepth views are synthesised from LowDepth<k> exactly as Downsample1/2 would have
  * written them (including the padding texels). */
 int meao_get_buffer(MeaoCtx *ctx, int32_t buffer_id, void *host_out, size_t host_bytes);
-/* Test hook: overwrite an intermediate (ids 1-5, 10-17) from host data in the same format. */
+/* Test hook: overwrite an intermediate (ids 1-5, 10-21) from host data in the same format. */
 int meao_set_buffer(MeaoCtx *ctx, int32_t buffer_id, const void *host_in, size_t host_bytes);
+/* replaces: PushDebugBlitCommands (AO.cs:787-820) + the debug composite, Blit.shader pass 3 (:116-134): writes the
+ * width x height R8 image that _result holds after the debug blit of buffer <buffer_id> (1..17, the `debug` property
+ * AO.cs:60; 18..21 for the HighQuality extension) into out_r8_dev (tight rows).  Non-tiled sources: cmd.Blit(rt, _result),
+ * a point-sampled stretch (texel = floor(uv * size) at the pixel centre); TiledDepth1..4: Blit.shader pass 4 "Detile"
+ * (:136-156), a 4 x 4 mosaic of the 16 slices; 17: the AO texture itself.  Asynchronous on `stream`. */
+int meao_debug_view(MeaoCtx *ctx, int32_t buffer_id, void *out_r8_dev, void *stream);
 
 /* ---- CPU-side constants, exposed so they can be checked against the reference math ------------- */
 /* out[0..11] gInvThicknessTable, out[12..23] gSampleWeightTable, out[24..25] gInvSliceDimension,
  * out[26] gRejectFadeoff, out[27] gIntensity            (AO.cs:678-734) */
 int meao_render_constants(MeaoCtx *ctx, int32_t level, float out28[28]);
+/* same layout for the non-tiled dispatch of meao_stage_render_wide (source = LowDepth<level>, AO.cs:679 applied) */
+int meao_render_constants_wide(MeaoCtx *ctx, int32_t level, float out28[28]);
 /* out[0..1] InvLowResolution, out[2..3] InvHighResolution, out[4] NoiseFilterStrength, out[5] StepSize,
  * out[6] kBlurTolerance, out[7] kUpsampleTolerance       (AO.cs:760-771) */
 int meao_upsample_constants(MeaoCtx *ctx, int32_t lo_level, float out8[8]);
@@ -224,7 +256,7 @@ MeaoRenderEventFunc meao_get_render_event_func(void);
 
 /* ---- introspection ------------------------------------------------------------------------------ */
 int64_t meao_launch_count(const MeaoCtx *ctx);       /* kernels launched (or replayed via graph) so far */
-int meao_kernels_per_frame(const MeaoCtx *ctx);      /* kernel nodes in one frame */
+int meao_kernels_per_frame(const MeaoCtx *ctx);      /* kernel nodes in one frame: 9 + one per bit of high_quality_mask */
 /* Algorithmic bytes of the reference data-flow: stage 0 = whole frame, 1 = Downsample1,
  * 2 = Downsample2, 3 = Render x4, 4 = Upsample x4, 5 = final Upsample (L1->L0) only. */
 int64_t meao_algorithmic_bytes(const MeaoCtx *ctx, int32_t stage);

@@ -29,6 +29,10 @@ class MeaoDeviceCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32)]
 
 
+class MeaoVariants(C.Structure):
+    _fields_ = [("single_pass_stereo", C.c_int32), ("sample_exhaustively", C.c_int32), ("high_quality_mask", C.c_int32)]
+
+
 class MeaoBufferDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("slices", C.c_int32), ("elem_bytes", C.c_int32)]
 
@@ -44,6 +48,8 @@ SIGNATURES = {
     "meao_set_params": (C.c_int, [C.c_void_p, C.POINTER(MeaoParams)]),
     "meao_get_params": (C.c_int, [C.c_void_p, C.POINTER(MeaoParams)]),
     "meao_default_params": (None, [C.POINTER(MeaoParams)]),
+    "meao_set_variants": (C.c_int, [C.c_void_p, C.POINTER(MeaoVariants)]),
+    "meao_get_variants": (C.c_int, [C.c_void_p, C.POINTER(MeaoVariants)]),
     "meao_set_camera": (C.c_int, [C.c_void_p, C.POINTER(MeaoCamera)]),
     "meao_resize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "meao_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -55,11 +61,14 @@ SIGNATURES = {
     "meao_host_free": (None, [C.c_void_p]),
     "meao_stage_downsample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "meao_stage_render": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "meao_stage_render_wide": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "meao_stage_upsample": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "meao_buffer_desc": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(MeaoBufferDesc)]),
     "meao_get_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
     "meao_set_buffer": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
     "meao_render_constants": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),
+    "meao_render_constants_wide": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),
+    "meao_debug_view": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "meao_upsample_constants": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),
     "meao_zbuffer_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "meao_set_row_band": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

@@ -25,6 +25,8 @@ class Camera:
     farClipPlane: float = 100.0
     fieldOfView: float = 60.0           # vertical, degrees
     usesReversedZBuffer: bool = True    # SystemInfo.usesReversedZBuffer on D3D11/12
+    stereoEnabled: bool = False         # Camera.stereoEnabled (AO.cs:397)
+    targetTexture: object = None        # Camera.targetTexture (AO.cs:398)
 
     @property
     def aspect(self) -> float:
@@ -47,7 +49,9 @@ class AmbientOcclusion:
     DEBUG_NAMES = {1: "LinearDepth", 2: "LowDepth1", 3: "LowDepth2", 4: "LowDepth3", 5: "LowDepth4",
                    6: "TiledDepth1", 7: "TiledDepth2", 8: "TiledDepth3", 9: "TiledDepth4",
                    10: "Occlusion1", 11: "Occlusion2", 12: "Occlusion3", 13: "Occlusion4",
-                   14: "Combined1", 15: "Combined2", 16: "Combined3", 17: "AmbientOcclusion"}
+                   14: "Combined1", 15: "Combined2", 16: "Combined3", 17: "AmbientOcclusion",
+                   # extension ids: HighQuality<k>, the output of Render.compute kernel "main" (highQualityMask)
+                   18: "HighQuality1", 19: "HighQuality2", 20: "HighQuality3", 21: "HighQuality4"}
 
     def __init__(self, camera: Camera, device: int = 0, use_graph: bool = True):
         self._lib = N.lib()
@@ -70,6 +74,11 @@ class AmbientOcclusion:
         self._intensity = p.intensity
         self._debug = 0
         self._ambientOnly = True
+        # shader variants the reference ships but never selects; defaults = reference behaviour
+        self.sampleExhaustively = False     # Render.compute:144-159
+        self.highQualityMask = 0            # bit k-1: Render.compute kernel "main" on level k + Upsample main_premin*
+        self._drawCountPerFrame = 0         # AO.cs:289: used to detect single-pass stereo
+        self._stereo = False                # singlePassStereoEnabled as latched by the last LateUpdate
         self.rebuild_count = 0
         self._width = self._height = 0
 
@@ -101,18 +110,42 @@ class AmbientOcclusion:
     def _check(self, rc: int) -> int:
         return N.check(self._ctx, rc)
 
+    # ---- single-pass stereo detection (AO.cs:352-355, 387-401) ------------------------------------------
+    def OnPreRender(self) -> None:
+        """Unity calls this once per camera draw; with single-pass stereo both eyes are ONE draw (AO.cs:352-355)."""
+        self._drawCountPerFrame += 1
+
+    @property
+    def singlePassStereoEnabled(self) -> bool:
+        cam = self._camera
+        return bool(cam is not None and cam.stereoEnabled and cam.targetTexture is None and self._drawCountPerFrame == 1)
+
     # ---- LateUpdate: re-plan only when something changed (AO.cs:329-350) ---------------------------
     def LateUpdate(self) -> bool:
+        """Once per frame (AO.cs:329-350); render() / render_host() call it themselves.  Returns True when it re-planned."""
+        return self._update(True)
+
+    def _update(self, frame: bool) -> bool:
+        """The body of LateUpdate.  frame=False (debug / stage / constant queries between two frames) skips the
+        per-frame reset of the draw counter (AO.cs:349), so such calls do not toggle the stereo detection."""
         cam = self._camera
         p = N.MeaoParams(self._noiseFilterTolerance, self._blurTolerance, self._upsampleTolerance,
                          self._thicknessModifier, self._intensity, self._debug, int(self._ambientOnly))
         rebuild = self._check(self._lib.meao_set_params(self._ctx, C.byref(p))) == 1      # CheckPropertiesChanged
         c = N.MeaoCamera(cam.nearClipPlane, cam.farClipPlane, 1.0 / cam.projection00, int(cam.usesReversedZBuffer))
         self._check(self._lib.meao_set_camera(self._ctx, C.byref(c)))
-        resized = self._check(self._lib.meao_resize(self._ctx, cam.pixelWidth, cam.pixelHeight)) == 1  # CheckBaseDimensions
-        self._width, self._height = cam.pixelWidth, cam.pixelHeight
+        if frame:
+            self._stereo = self.singlePassStereoEnabled       # evaluated once per frame, before the counter reset (AO.cs:338-349)
+        stereo = self._stereo
+        v = N.MeaoVariants(int(stereo), int(self.sampleExhaustively), int(self.highQualityMask))
+        rebuild |= self._check(self._lib.meao_set_variants(self._ctx, C.byref(v))) == 1
+        width = cam.pixelWidth * (2 if stereo else 1)                                                # AO.cs:338-341, 501-504
+        resized = self._check(self._lib.meao_resize(self._ctx, width, cam.pixelHeight)) == 1          # CheckBaseDimensions
+        self._width, self._height = width, cam.pixelHeight
         if rebuild or resized:
             self.rebuild_count += 1
+        if frame:
+            self._drawCountPerFrame = 0                                                              # AO.cs:349
         return rebuild or resized
 
     # ---- frame ----------------------------------------------------------------------------------
@@ -210,21 +243,26 @@ class AmbientOcclusion:
 
     # ---- stage entry points (mirror Push*Commands) -----------------------------------------------
     def stage_downsample(self, depth, *, linear: bool = False) -> None:
-        self.LateUpdate()
+        self._update(False)
         kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
         self._check(self._lib.meao_stage_downsample(self._ctx, depth.data_ptr(), kind, self._stream()))
 
     def stage_render(self, level: int) -> None:
-        self.LateUpdate()
+        self._update(False)
         self._check(self._lib.meao_stage_render(self._ctx, level, self._stream()))
 
+    def stage_render_wide(self, level: int) -> None:
+        """PushRenderCommands for the non-tiled source LowDepth<level> (kernel "main") -> HighQuality<level>."""
+        self._update(False)
+        self._check(self._lib.meao_stage_render_wide(self._ctx, level, self._stream()))
+
     def stage_upsample(self, lo_level: int) -> None:
-        self.LateUpdate()
+        self._update(False)
         self._check(self._lib.meao_stage_upsample(self._ctx, lo_level, None, self._stream()))
 
     # ---- debug views (AO.cs:787-820) ---------------------------------------------------------------
     def buffer_desc(self, debug_id: int) -> N.MeaoBufferDesc:
-        self.LateUpdate()
+        self._update(False)
         d = N.MeaoBufferDesc()
         self._check(self._lib.meao_buffer_desc(self._ctx, debug_id, C.byref(d)))
         return d
@@ -238,6 +276,25 @@ class AmbientOcclusion:
         self._check(self._lib.meao_get_buffer(self._ctx, debug_id, a.ctypes.data, a.nbytes))
         return a
 
+    def debug_view(self, debug_id: int, out=None, *, stream=None):
+        """PushDebugBlitCommands (AO.cs:787-820): the W x H R8 image the `debug` property would put on screen for
+        buffer <debug_id>; returns a CUDA uint8 tensor [H, W]."""
+        import torch
+        self._update(False)
+        if out is None:
+            out = torch.empty((self._height, self._width), dtype=torch.uint8, device=f"cuda:{self.device}")
+        self._check(self._lib.meao_debug_view(self._ctx, debug_id, out.data_ptr(), self._stream(stream)))
+        return out
+
+    def dump_debug_view(self, debug_id: int, path: str) -> None:
+        """Writes the debug view as a binary PGM (P5) image -- the observable twin of the inspector's debug slider."""
+        img = self.debug_view(debug_id)
+        self.synchronize()
+        a = img.cpu().numpy()
+        with open(path, "wb") as f:
+            f.write(b"P5\n%d %d\n255\n" % (a.shape[1], a.shape[0]))
+            f.write(a.tobytes())
+
     def set_debug_buffer(self, debug_id: int, values: np.ndarray) -> None:
         d = self.buffer_desc(debug_id)
         dt = {1: np.uint8, 2: np.float16, 4: np.float32}[d.elem_bytes]
@@ -246,16 +303,17 @@ class AmbientOcclusion:
         self._check(self._lib.meao_set_buffer(self._ctx, debug_id, a.ctypes.data, a.nbytes))
 
     # ---- constants ----------------------------------------------------------------------------------
-    def render_constants(self, level: int) -> dict:
-        self.LateUpdate()
+    def render_constants(self, level: int, wide: bool = False) -> dict:
+        self._update(False)
         out = (C.c_float * 28)()
-        self._check(self._lib.meao_render_constants(self._ctx, level, out))
+        fn = self._lib.meao_render_constants_wide if wide else self._lib.meao_render_constants
+        self._check(fn(self._ctx, level, out))
         a = np.array(out, np.float32)
         return {"inv_thickness": a[0:12], "sample_weight": a[12:24], "inv_slice_dim": a[24:26],
                 "reject_fadeoff": a[26], "intensity": a[27]}
 
     def upsample_constants(self, lo_level: int) -> dict:
-        self.LateUpdate()
+        self._update(False)
         out = (C.c_float * 8)()
         self._check(self._lib.meao_upsample_constants(self._ctx, lo_level, out))
         a = np.array(out, np.float32)
@@ -263,14 +321,14 @@ class AmbientOcclusion:
                 "blur_tolerance": a[6], "upsample_tolerance": a[7]}
 
     def zbuffer_params(self) -> np.ndarray:
-        self.LateUpdate()
+        self._update(False)
         out = (C.c_float * 4)()
         self._check(self._lib.meao_zbuffer_params(self._ctx, out))
         return np.array(out, np.float32)
 
     # ---- row bands (multi-GPU frame partition) ---------------------------------------------------
     def set_row_band(self, row0: int, row1: int, prev_row0: int = -1, next_row1: int = -1) -> None:
-        self.LateUpdate()
+        self._update(False)
         self._check(self._lib.meao_set_row_band(self._ctx, row0, row1, prev_row0, next_row1))
         self._band = (row0, row1)
 
@@ -280,7 +338,7 @@ class AmbientOcclusion:
 
     def band_rows(self) -> dict:
         """Row ranges of this band per level: rows to produce, LowDepth rows read, LowDepth rows owned."""
-        self.LateUpdate()
+        self._update(False)
         out = (C.c_int32 * 30)()
         self._check(self._lib.meao_band_rows(self._ctx, out))
         a = list(out)
@@ -334,18 +392,18 @@ class AmbientOcclusion:
         return self._lib.meao_kernels_per_frame(self._ctx)
 
     def algorithmic_bytes(self, stage: int = 0) -> int:
-        self.LateUpdate()
+        self._update(False)
         return self._check(self._lib.meao_algorithmic_bytes(self._ctx, stage))
 
     def selftest_div(self, n: int = 1 << 28, seed: int = 1) -> int:
         """Mismatches between the kernels' guarded fast division / reciprocal and the IEEE operators (must be 0)."""
-        self.LateUpdate()
+        self._update(False)
         m = C.c_uint64(0)
         self._check(self._lib.meao_selftest_div(self._ctx, n, seed, C.byref(m)))
         return int(m.value)
 
     def profile_frame(self, depth, out, *, linear: bool = False) -> list[tuple[str, float]]:
-        self.LateUpdate()
+        self._update(False)
         n = self.kernels_per_frame
         ms = (C.c_float * n)()
         names = (C.c_char_p * n)()

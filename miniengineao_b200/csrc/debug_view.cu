@@ -1,0 +1,54 @@
+// debug_view.cu -- the debug views of the AmbientOcclusion component.
+//
+// Replaces PushDebugBlitCommands (AmbientOcclusion.cs:787-820): cmd.Blit(rt, _result) for a non-tiled buffer
+// (point-sampled stretch: the RTs are FilterMode.Point, AO.cs:206,228,236) or Blit.shader pass 4 "Detile"
+// (:136-156) for a TiledDepth atlas, followed by the R8 store of the _result target (AO.cs:475).  The raster
+// passes sample at the pixel centre uv = ((x + .5) / W, (y + .5) / H); texel indices are evaluated in exact
+// integer arithmetic (floor((2x+1) * sw / (2W))), which is what an exact rasteriser + point sampler yields.
+//
+// The TiledDepth atlases are virtual here: slice s, texel (tx, ty) is natural pixel
+// (4 tx + (s & 3), 4 ty + (s >> 2)) of LowDepth<k> rounded to f16, or the padding value outside the level.
+// Bound: HBM (1 B written per pixel, <= 4 B read per source texel); not on the frame path.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace meao {
+
+namespace {
+
+__global__ void __launch_bounds__(256) debug_view_kernel(const DebugViewArgs a)
+{
+#ifdef MEAO_DEVICE_OK
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= a.W) return;
+    float v;
+    if (a.tiled) {
+        // Blit.shader:150-152: uv4 = uv * 4; slice = floor(uv4.x) + floor(uv4.y) * 4; sample the slice at frac(uv4)
+        const long long nx = 8LL * x + 4, ny = 8LL * y + 4;                 // 4 * uv = n / (2 * size)
+        const int qx = (int)(nx / (2LL * a.W)), qy = (int)(ny / (2LL * a.H));
+        const long long rx = nx - 2LL * a.W * qx, ry = ny - 2LL * a.H * qy; // frac = r / (2 * size)
+        const int tx = (int)(rx * a.sw / (2LL * a.W)), ty = (int)(ry * a.sh / (2LL * a.H));
+        const int px = 4 * tx + qx, py = 4 * ty + qy;                       // inverse of DS1:69,71 with slice = qx | qy << 2
+        v = a.pad;
+        if (px < a.lw && py < a.lh) v = f16_round(reinterpret_cast<const float *>(a.src)[(size_t)py * a.spitch + px]);
+    } else {
+        // cmd.Blit(rt, _result), AO.cs:817
+        const int tx = (int)((2LL * x + 1) * a.sw / (2LL * a.W)), ty = (int)((2LL * y + 1) * a.sh / (2LL * a.H));
+        const size_t i = (size_t)ty * a.spitch + tx;
+        if (a.elem == 1) { a.out[(size_t)y * a.out_pitch + x] = reinterpret_cast<const uint8_t *>(a.src)[i]; return; }   // R8 -> R8: store(load(k)) == k
+        v = (a.elem == 2) ? __half2float(reinterpret_cast<const __half *>(a.src)[i]) : reinterpret_cast<const float *>(a.src)[i];
+    }
+    a.out[(size_t)y * a.out_pitch + x] = (uint8_t)unorm8_code(v);
+#endif
+}
+
+}  // namespace
+
+cudaError_t launch_debug_view(const DebugViewArgs &a, cudaStream_t s)
+{
+    dim3 grid(ceil_div(a.W, 256), a.H);
+    debug_view_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace meao

@@ -40,18 +40,22 @@ struct RenderArgs {
     int opitch;
     int sw, sh;             // size of the (virtual) TiledDepth<k> slice = level k+2
     float pad;              // value of atlas padding texels (already f16-rounded): Linearize(0) for k=1,2; 0 for k=3,4
-    float inv_thickness[7]; // gInvThicknessTable entries used by Render.compute:162-168, in call order
-    float neg_front[7];     // -(invThickness - 0.5)  (Render.compute:85)
-    float weight[7];        // gSampleWeightTable entries, same order
+    float inv_thickness[12];// gInvThicknessTable entries in CALL order: 7 used by Render.compute:162-168 (checker), 12 by :148-159 (exhaustive)
+    float neg_front[12];    // -(invThickness - 0.5)  (Render.compute:85)
+    float weight[12];       // gSampleWeightTable entries, same order
     float reject_fadeoff;   // gRejectFadeoff
     float intensity;        // gIntensity
     int row0, row1;         // output rows (level k) to produce
+    int wide;               // 0: kernel main_interleaved (virtual f16 atlas of level k+2); 1: kernel main (WIDE_SAMPLING on f32 LowDepth<k>;
+                            //    sw/sh/pad unused, low_map must carry the kRenderWideBox box)
+    int exhaustive;         // SAMPLE_EXHAUSTIVELY (Render.compute:144-159)
 };
 cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const RenderArgs &a, cudaStream_t s);
 #ifndef MEAO_REN_TH
 #define MEAO_REN_TH 32
 #endif
 constexpr int kRenderBoxW = 96, kRenderBoxH = MEAO_REN_TH + 32;     // TMA box of the render kernel (f32 elements)
+constexpr int kRenderWideBoxW = 80, kRenderWideBoxH = MEAO_REN_TH + 16;   // ... of its WIDE_SAMPLING variant (apron 8)
 
 // ---- stage 3: blur_upsample = Upsample.compute main / main_blendout, one level ----------------
 struct UpsampleArgs {
@@ -73,14 +77,32 @@ struct UpsampleArgs {
     int fast_div_ok;        // upsample_tolerance and noise_filter_strength are positive normals in [2^-60, 2^60)
     int row0, row1;         // output rows (hi level) to produce
 };
-cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensorMap &lo_ao_map, bool use_tma,
-                                 const UpsampleArgs &a, cudaStream_t s);
+// main_premin / main_premin_blendout (COMBINE_LOWER_RESOLUTIONS): the same arguments plus LoResAO2 = HighQuality<lo>
+struct UpsamplePreminArgs { UpsampleArgs base; const uint8_t *lo_ao2; int lo_a2pitch; };
+// lo_ao2 == nullptr: kernels main / main_blendout; otherwise the premin kernels (lo_ao2_map = its TMA descriptor)
+cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensorMap &lo_ao_map, const CUtensorMap *lo_ao2_map, bool use_tma,
+                                 const UpsampleArgs &a, const uint8_t *lo_ao2, int lo_a2pitch, cudaStream_t s);
 constexpr int kUpsDepthBoxW = 40, kUpsDepthBoxH = 22; // TMA boxes of the upsample kernel
 constexpr int kUpsAoBoxW = 64, kUpsAoBoxH = 22;
 
 // ---- debug: synthesise a TiledDepth<k> view (reference layout [16][sh][sw], f16 bits) ----------
 cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int sw, int sh, float pad,
                                __half *out, cudaStream_t s);
+
+// ---- debug views (PushDebugBlitCommands AO.cs:787-820, Blit.shader pass 4): buffer -> W x H R8 image ----------
+struct DebugViewArgs {
+    const void *src;        // non-tiled: the buffer itself; tiled: LowDepth<k> (the atlas is virtual)
+    int elem;               // bytes per source element: 1 unorm8, 2 f16, 4 f32
+    int sw, sh;             // source texture size (tiled: size of one slice)
+    int spitch;             // source pitch in elements
+    int tiled;              // 1: TiledDepth<k> view synthesised from LowDepth<k>
+    int lw, lh;             // tiled: size of level k
+    float pad;              // tiled: value of the atlas padding texels (f16-rounded)
+    uint8_t *out;           // W x H R8 codes
+    int out_pitch;
+    int W, H;
+};
+cudaError_t launch_debug_view(const DebugViewArgs &a, cudaStream_t s);
 
 // ---- composite (Blit.shader passes 1 and 2): colour *= ao, 4 pixels per thread ------------------------
 cudaError_t launch_composite(const uint8_t *ao, void *color, long long npix, int half, int rgb, int alpha, int one_minus, cudaStream_t s);

@@ -46,6 +46,8 @@ struct Plan {
     float reject_fadeoff;
     float intensity;
     float pad[5];
+    float inv_thickness_wide[5][12];       // the same for a NON-tiled source LowDepth<k> (kernel "main", AO.cs:679)
+    float inv_slice_dim_wide[5][2];
     // Upsample (per lo level 1..4) -- AO.cs:750-771
     float inv_low[5][2], inv_high[5][2];
     float noise_filter_strength[5], step_size[5], blur_tolerance[5], upsample_tolerance[5];
@@ -66,6 +68,7 @@ struct MeaoCtx {
 
     MeaoParams params;
     MeaoCamera camera;
+    MeaoVariants variants = {0, 0, 0};
     bool plan_dirty = true;
     Plan plan;
 
@@ -81,6 +84,7 @@ struct MeaoCtx {
     float *low[5] = {nullptr}; int low_pitch[5] = {0};
     uint8_t *occ[5] = {nullptr}; int occ_pitch[5] = {0};
     uint8_t *comb[4] = {nullptr};           // same pitch as occ of that level
+    uint8_t *hq[5] = {nullptr};             // HighQuality<k> (kernel "main" output), same pitch as occ of that level
     uint8_t *result = nullptr; int result_pitch = 0;
     // staging for the host path: two slots so that the H2D copy of frame i+1 overlaps the kernels and the
     // D2H copy of frame i (meao_render_host_async)
@@ -95,6 +99,8 @@ struct MeaoCtx {
     CUtensorMap map_low_ren[5];             // LowDepth<k> with the render box
     CUtensorMap map_low_ups[5];             // LowDepth<k> with the upsample depth box
     CUtensorMap map_ao_ups[5];              // lo AO of upsample lo level k (Occlusion4 / Combined k)
+    CUtensorMap map_low_wide[5];            // LowDepth<k> with the wide-render box
+    CUtensorMap map_hq_ups[5];              // HighQuality<k> as LoResAO2 of upsample lo level k
 
     // row ranges (per level) for this band
     Range need_c[5];                        // rows of Occlusion<k>/Combined<k> to produce (k=1..4); [0] = final rows
@@ -158,12 +164,21 @@ void build_plan(MeaoCtx *c)
         const int src_w = c->lw[k + 2], src_h = c->lh[k + 2];
         const float ScreenspaceDiameter = 10;                                                        // AO.cs:669
         float ThicknessMultiplier = 2 * c->camera.tan_half_fov_h * ScreenspaceDiameter / src_w;     // AO.cs:678
+        if (c->variants.single_pass_stereo) ThicknessMultiplier *= 2;                                // AO.cs:680
         float InverseRangeFactor = 1 / ThicknessMultiplier;                                          // AO.cs:683
         for (int i = 0; i < 12; i++) p.inv_thickness[k][i] = InverseRangeFactor / thick[i];          // AO.cs:687-688
+        {   // the same recorder fed a non-tiled source (LowDepth<k>): kernel "main"
+            float tm = 2 * c->camera.tan_half_fov_h * ScreenspaceDiameter / c->lw[k];               // AO.cs:678
+            tm *= 2;                                                                                 // AO.cs:679 (!source.isTiled)
+            if (c->variants.single_pass_stereo) tm *= 2;                                             // AO.cs:680
+            const float irf = 1 / tm;                                                                // AO.cs:683
+            for (int i = 0; i < 12; i++) p.inv_thickness_wide[k][i] = irf / thick[i];
+            p.inv_slice_dim_wide[k][0] = 1.0f / c->lw[k]; p.inv_slice_dim_wide[k][1] = 1.0f / c->lh[k];
+        }
         static const float mult[12] = {4, 4, 4, 4, 4, 8, 8, 8, 4, 8, 8, 4};                          // AO.cs:696-707
         float *w = p.sample_weight[k];
         for (int i = 0; i < 12; i++) w[i] = mult[i] * thick[i];
-        w[0] = 0; w[2] = 0; w[5] = 0; w[7] = 0; w[9] = 0;                                            // AO.cs:711-715
+        if (!c->variants.sample_exhaustively) { w[0] = 0; w[2] = 0; w[5] = 0; w[7] = 0; w[9] = 0; }  // AO.cs:709-715
         float total = 0.0f;
         for (int i = 0; i < 12; i++) total += w[i];                                                  // AO.cs:718-721
         for (int i = 0; i < 12; i++) w[i] /= total;                                                  // AO.cs:723-724
@@ -294,13 +309,14 @@ int allocate(MeaoCtx *c)
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     size_t o_lin = take((size_t)c->lin_pitch * c->lh[0] * sizeof(__half));
     size_t o_res = take((size_t)c->result_pitch * c->lh[0]);
-    size_t o_low[5], o_occ[5], o_comb[4];
+    size_t o_low[5], o_occ[5], o_comb[4], o_hq[5];
     for (int k = 1; k <= 4; k++) {
         c->low_pitch[k] = align_up(c->lw[k], 32);
         c->occ_pitch[k] = align_up(c->lw[k], 128);
         o_low[k] = take((size_t)c->low_pitch[k] * c->lh[k] * sizeof(float));
         o_occ[k] = take((size_t)c->occ_pitch[k] * c->lh[k]);
         if (k <= 3) o_comb[k] = take((size_t)c->occ_pitch[k] * c->lh[k]);
+        o_hq[k] = take((size_t)c->occ_pitch[k] * c->lh[k]);
     }
     size_t o_dst[2], o_ast[2];
     for (int i = 0; i < 2; i++) { o_dst[i] = take((size_t)W * H * sizeof(float)); o_ast[i] = take((size_t)W * H); }
@@ -317,6 +333,7 @@ int allocate(MeaoCtx *c)
         c->low[k] = (float *)(b + o_low[k]);
         c->occ[k] = (uint8_t *)(b + o_occ[k]);
         if (k <= 3) c->comb[k] = (uint8_t *)(b + o_comb[k]);
+        c->hq[k] = (uint8_t *)(b + o_hq[k]);
     }
     for (int i = 0; i < 2; i++) { c->depth_stage[i] = (float *)(b + o_dst[i]); c->ao_stage[i] = (uint8_t *)(b + o_ast[i]); }
 
@@ -328,6 +345,8 @@ int allocate(MeaoCtx *c)
             ok &= make_map(c, &c->map_low_ups[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], kUpsDepthBoxW, kUpsDepthBoxH) == 0;
             uint8_t *ao = (k == 4) ? c->occ[4] : c->comb[k];
             ok &= make_map(c, &c->map_ao_ups[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ao, c->lw[k], c->lh[k], c->occ_pitch[k], kUpsAoBoxW, kUpsAoBoxH) == 0;
+            ok &= make_map(c, &c->map_low_wide[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], kRenderWideBoxW, kRenderWideBoxH) == 0;
+            ok &= make_map(c, &c->map_hq_ups[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c->hq[k], c->lw[k], c->lh[k], c->occ_pitch[k], kUpsAoBoxW, kUpsAoBoxH) == 0;
         }
         c->tma_ok = ok;
     }
@@ -335,6 +354,8 @@ int allocate(MeaoCtx *c)
         memset(c->map_low_ren, 0, sizeof c->map_low_ren);
         memset(c->map_low_ups, 0, sizeof c->map_low_ups);
         memset(c->map_ao_ups, 0, sizeof c->map_ao_ups);
+        memset(c->map_low_wide, 0, sizeof c->map_low_wide);
+        memset(c->map_hq_ups, 0, sizeof c->map_hq_ups);
     }
     return setup_band(c);
 }
@@ -372,27 +393,36 @@ int record_downsample(MeaoCtx *c, const void *depth, int kind, cudaStream_t s)
     return 0;
 }
 
-// PushRenderCommands, AO.cs:660-748
-int record_render(MeaoCtx *c, int k, int kind, cudaStream_t s)
+// PushRenderCommands, AO.cs:660-748.  wide = false: the call AmbientOcclusion.cs makes (tiled source, kernel main_interleaved);
+// wide = true: the same recorder for the non-tiled source LowDepth<k> (kernel main) -> HighQuality<k>.
+int record_render(MeaoCtx *c, int k, int kind, cudaStream_t s, bool wide = false)
 {
-    static const int idx[7] = {1, 3, 4, 8, 11, 6, 10};       // Render.compute:162-168 table slots
+    static const int idx_checker[7] = {1, 3, 4, 8, 11, 6, 10};                       // Render.compute:162-168 table slots, call order
+    static const int idx_exh[12] = {0, 1, 2, 3, 4, 8, 11, 5, 6, 7, 9, 10};           // Render.compute:148-159
+    const bool exh = c->variants.sample_exhaustively != 0;
+    const int n = exh ? 12 : 7;
+    const int *idx = exh ? idx_exh : idx_checker;
     RenderArgs a{};
     a.low = c->low[k]; a.lw = c->lw[k]; a.lh = c->lh[k]; a.lpitch = c->low_pitch[k];
-    a.occ = c->occ[k]; a.opitch = c->occ_pitch[k];
+    a.occ = wide ? c->hq[k] : c->occ[k]; a.opitch = c->occ_pitch[k];
     a.sw = c->lw[k + 2]; a.sh = c->lh[k + 2];
     a.pad = host_f16_round((kind != MEAO_DEPTH_LINEAR_F32) ? c->plan.pad[k] : 0.0f);
-    for (int i = 0; i < 7; i++) {
-        a.inv_thickness[i] = c->plan.inv_thickness[k][idx[i]];
+    const float *it = wide ? c->plan.inv_thickness_wide[k] : c->plan.inv_thickness[k];
+    for (int i = 0; i < n; i++) {
+        a.inv_thickness[i] = it[idx[i]];
         a.neg_front[i] = -(a.inv_thickness[i] - 0.5f);                                               // Render.compute:85
         a.weight[i] = c->plan.sample_weight[k][idx[i]];
     }
     a.reject_fadeoff = c->plan.reject_fadeoff;
     a.intensity = c->plan.intensity;
     a.row0 = c->need_c[k].lo; a.row1 = c->need_c[k].hi;
-    CUDA_TRY(c, launch_render_ao(c->map_low_ren[k], c->tma_ok, a, s));
+    a.wide = wide ? 1 : 0;
+    a.exhaustive = exh ? 1 : 0;
+    CUDA_TRY(c, launch_render_ao(wide ? c->map_low_wide[k] : c->map_low_ren[k], c->tma_ok, a, s));
     c->launches++;
     return 0;
 }
+inline bool hq_level(const MeaoCtx *c, int k) { return ((c->variants.high_quality_mask >> (k - 1)) & 1) != 0; }
 
 // PushUpsampleCommands with the wiring of AO.cs:528-531
 int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
@@ -419,7 +449,8 @@ int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
         a.fast_div_ok = safe(a.upsample_tolerance) && safe(a.noise_filter_strength);
     }
     a.row0 = c->need_c[hi].lo; a.row1 = c->need_c[hi].hi;
-    CUDA_TRY(c, launch_blur_upsample(c->map_low_ups[lo], c->map_ao_ups[lo], c->tma_ok, a, s));
+    const uint8_t *lo_ao2 = hq_level(c, lo) ? c->hq[lo] : nullptr;                   // kernels main_premin / main_premin_blendout
+    CUDA_TRY(c, launch_blur_upsample(c->map_low_ups[lo], c->map_ao_ups[lo], &c->map_hq_ups[lo], c->tma_ok, a, lo_ao2, c->occ_pitch[lo], s));
     c->launches++;
     return 0;
 }
@@ -436,12 +467,17 @@ int record_frame_dag(MeaoCtx *c, const void *depth, int kind, void *ao_out, cuda
     CUDA_TRY(c, cudaStreamWaitEvent(b1, c->ev[0], 0));
     CUDA_TRY(c, cudaStreamWaitEvent(b2, c->ev[0], 0));
     CUDA_TRY(c, cudaStreamWaitEvent(b3, c->ev[0], 0));
+    // the optional high-quality render of a level (kernel "main") rides on the branch of that level's interleaved render
     if ((rc = record_render(c, 1, kind, s))) return rc;
+    if (hq_level(c, 1) && (rc = record_render(c, 1, kind, s, true))) return rc;
     if ((rc = record_render(c, 2, kind, b1))) return rc;
+    if (hq_level(c, 2) && (rc = record_render(c, 2, kind, b1, true))) return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[1], b1));
     if ((rc = record_render(c, 3, kind, b2))) return rc;
+    if (hq_level(c, 3) && (rc = record_render(c, 3, kind, b2, true))) return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[2], b2));
     if ((rc = record_render(c, 4, kind, b3))) return rc;
+    if (hq_level(c, 4) && (rc = record_render(c, 4, kind, b3, true))) return rc;
     CUDA_TRY(c, cudaStreamWaitEvent(b3, c->ev[2], 0));
     if ((rc = record_upsample(c, 4, nullptr, b3))) return rc;
     CUDA_TRY(c, cudaStreamWaitEvent(b3, c->ev[1], 0));
@@ -456,16 +492,19 @@ int record_frame_dag(MeaoCtx *c, const void *depth, int kind, void *ao_out, cuda
 // record order of RebuildCommandBuffers, AO.cs:511-531
 int record_frame(MeaoCtx *c, const void *depth, int kind, void *ao_out, cudaStream_t s, bool profile)
 {
-    static const char *names[10] = {"prepare_depth", "render_ao L1", "render_ao L2", "render_ao L3", "render_ao L4",
-                                    "blur_upsample L4->L3", "blur_upsample L3->L2", "blur_upsample L2->L1", "blur_upsample L1->L0", ""};
+    static const char *ren_names[5] = {"", "render_ao L1", "render_ao L2", "render_ao L3", "render_ao L4"};
+    static const char *hq_names[5] = {"", "render_ao_wide L1", "render_ao_wide L2", "render_ao_wide L3", "render_ao_wide L4"};
+    static const char *ups_names[5] = {"", "blur_upsample L1->L0", "blur_upsample L2->L1", "blur_upsample L3->L2", "blur_upsample L4->L3"};
+    std::vector<const char *> names;
     std::vector<cudaEvent_t> ev;
     auto mark = [&]() { if (profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back(e); } };
     int rc;
     mark();
     if ((rc = record_downsample(c, depth, kind, s))) return rc;
-    mark();
-    for (int k = 1; k <= 4; k++) { if ((rc = record_render(c, k, kind, s))) return rc; mark(); }
-    for (int lo = 4; lo >= 1; lo--) { if ((rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s))) return rc; mark(); }
+    names.push_back("prepare_depth"); mark();
+    for (int k = 1; k <= 4; k++) { if ((rc = record_render(c, k, kind, s))) return rc; names.push_back(ren_names[k]); mark(); }
+    for (int k = 1; k <= 4; k++) if (hq_level(c, k)) { if ((rc = record_render(c, k, kind, s, true))) return rc; names.push_back(hq_names[k]); mark(); }
+    for (int lo = 4; lo >= 1; lo--) { if ((rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s))) return rc; names.push_back(ups_names[lo]); mark(); }
     if (profile) {
         CUDA_TRY(c, cudaStreamSynchronize(s));
         c->last_profile.clear();
@@ -486,6 +525,7 @@ int buffer_info(const MeaoCtx *c, int id, int *lvl, int *slices, int *elem)
     else if (id >= 10 && id <= 13) { *lvl = id - 9; *slices = 1; *elem = 1; }
     else if (id >= 14 && id <= 16) { *lvl = id - 13; *slices = 1; *elem = 1; }
     else if (id == 17) { *lvl = 0; *slices = 1; *elem = 1; }
+    else if (id >= 18 && id <= 21) { *lvl = id - 17; *slices = 1; *elem = 1; }      // HighQuality1..4 (extension)
     else return -1;
     (void)c;
     return 0;
@@ -499,6 +539,7 @@ int buffer_ptr(MeaoCtx *c, int id, void **p, size_t *pitch_bytes)
     else if (id >= 10 && id <= 13) { *p = c->occ[id - 9]; *pitch_bytes = c->occ_pitch[id - 9]; }
     else if (id >= 14 && id <= 16) { *p = c->comb[id - 13]; *pitch_bytes = c->occ_pitch[id - 13]; }
     else if (id == 17) { *p = c->result; *pitch_bytes = c->result_pitch; }
+    else if (id >= 18 && id <= 21) { *p = c->hq[id - 17]; *pitch_bytes = c->occ_pitch[id - 17]; }
     else return -1;
     return 0;
 }
@@ -616,6 +657,24 @@ int meao_get_params(const MeaoCtx *c, MeaoParams *out)
 {
     if (!c || !out) return MEAO_ERR_INVALID;
     *out = c->params;
+    return MEAO_OK;
+}
+
+int meao_set_variants(MeaoCtx *c, const MeaoVariants *v)
+{
+    if (!c || !v) return MEAO_ERR_INVALID;
+    if (v->high_quality_mask < 0 || v->high_quality_mask > 15) return fail(c, MEAO_ERR_INVALID, "high_quality_mask %d not in 0..15", v->high_quality_mask);
+    MeaoVariants n{v->single_pass_stereo ? 1 : 0, v->sample_exhaustively ? 1 : 0, v->high_quality_mask};
+    const bool changed = memcmp(&c->variants, &n, sizeof n) != 0;
+    c->variants = n;
+    if (changed) c->plan_dirty = true;          // re-plan + drop the captured graphs (ensure_ready)
+    return changed ? 1 : 0;
+}
+
+int meao_get_variants(const MeaoCtx *c, MeaoVariants *out)
+{
+    if (!c || !out) return MEAO_ERR_INVALID;
+    *out = c->variants;
     return MEAO_OK;
 }
 
@@ -742,6 +801,7 @@ int meao_render_band_finish(MeaoCtx *c, void *ao_out, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     const int kind = c->last_kind;
     for (int k = 1; k <= 4; k++) if ((rc = record_render(c, k, kind, s))) return rc;
+    for (int k = 1; k <= 4; k++) if (hq_level(c, k) && (rc = record_render(c, k, kind, s, true))) return rc;
     for (int lo = 4; lo >= 1; lo--) if ((rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s))) return rc;
     return MEAO_OK;
 }
@@ -816,7 +876,7 @@ int meao_band_phase_b(MeaoCtx *c, const void *recv_up, const void *recv_down, vo
     if (!ao_out) return fail(c, MEAO_ERR_INVALID, "ao_out is NULL");
     const int kind = c->last_kind;
     const MeaoCtx::GraphKey key{{recv_up, recv_down, ao_out, nullptr}, 200 + kind};
-    const int nk = 8 + ((recv_up || recv_down) ? 1 : 0);
+    const int nk = meao_kernels_per_frame(c) - 1 + ((recv_up || recv_down) ? 1 : 0);
     c->last_out = ao_out;
     return band_graph(c, key, (cudaStream_t)stream, nk, [&](cudaStream_t s) {
         int r = halo_kernel(c, (void *)recv_up, (void *)recv_down, false, s);
@@ -928,6 +988,13 @@ int meao_stage_render(MeaoCtx *c, int32_t level, void *stream)
     return record_render(c, level, c->last_kind, (cudaStream_t)stream);
 }
 
+int meao_stage_render_wide(MeaoCtx *c, int32_t level, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (level < 1 || level > 4) return fail(c, MEAO_ERR_INVALID, "render level %d not in 1..4", level);
+    return record_render(c, level, c->last_kind, (cudaStream_t)stream, true);
+}
+
 int meao_stage_upsample(MeaoCtx *c, int32_t lo_level, void *ao_out, void *stream)
 {
     int rc = ensure_ready(c); if (rc) return rc;
@@ -979,6 +1046,36 @@ int meao_get_buffer(MeaoCtx *c, int32_t id, void *host_out, size_t host_bytes)
     return MEAO_OK;
 }
 
+int meao_debug_view(MeaoCtx *c, int32_t id, void *out, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    int lvl, slices, elem;
+    if (!out || buffer_info(c, id, &lvl, &slices, &elem)) return fail(c, MEAO_ERR_INVALID, "bad buffer id %d / out is NULL", id);
+    if (c->band0 != 0 || c->band1 != c->H) return fail(c, MEAO_ERR_UNSUPPORTED, "debug views need a whole-frame context (no row band)");
+    cudaStream_t s = (cudaStream_t)stream;
+    DebugViewArgs a{};
+    a.W = c->W; a.H = c->H; a.out = (uint8_t *)out; a.out_pitch = c->W;
+    if (slices == 16) {                                             // AO.cs:810-814: Blit.shader pass 4
+        const int k = id - 5;
+        a.tiled = 1; a.src = c->low[k]; a.elem = 4; a.spitch = c->low_pitch[k];
+        a.sw = c->lw[k + 2]; a.sh = c->lh[k + 2]; a.lw = c->lw[k]; a.lh = c->lh[k];
+        a.pad = host_f16_round((c->last_kind != MEAO_DEPTH_LINEAR_F32) ? c->plan.pad[k] : 0.0f);
+    } else {                                                        // AO.cs:815-819
+        if (id == MEAO_BUF_AMBIENT_OCCLUSION && c->last_out) {
+            // the last frame wrote the AO texture straight into the caller's buffer: regenerate the context's own copy
+            const int64_t before = c->launches;
+            if ((rc = record_upsample(c, 1, nullptr, s))) return rc;
+            c->launches = before;
+        }
+        void *p; size_t pitch;
+        buffer_ptr(c, id, &p, &pitch);
+        a.src = p; a.elem = elem; a.spitch = (int)(pitch / elem); a.sw = c->lw[lvl]; a.sh = c->lh[lvl];
+    }
+    CUDA_TRY(c, launch_debug_view(a, s));
+    c->launches++;
+    return MEAO_OK;
+}
+
 int meao_set_buffer(MeaoCtx *c, int32_t id, const void *host_in, size_t host_bytes)
 {
     int rc = ensure_ready(c); if (rc) return rc;
@@ -1010,6 +1107,16 @@ int meao_render_constants(MeaoCtx *c, int32_t level, float out[28])
     memcpy(out, c->plan.inv_thickness[level], 48);
     memcpy(out + 12, c->plan.sample_weight[level], 48);
     out[24] = c->plan.inv_slice_dim[level][0]; out[25] = c->plan.inv_slice_dim[level][1];
+    out[26] = c->plan.reject_fadeoff; out[27] = c->plan.intensity;
+    return MEAO_OK;
+}
+
+int meao_render_constants_wide(MeaoCtx *c, int32_t level, float out[28])
+{
+    if (plan_only(c) || !out || level < 1 || level > 4) return MEAO_ERR_INVALID;
+    memcpy(out, c->plan.inv_thickness_wide[level], 48);
+    memcpy(out + 12, c->plan.sample_weight[level], 48);
+    out[24] = c->plan.inv_slice_dim_wide[level][0]; out[25] = c->plan.inv_slice_dim_wide[level][1];
     out[26] = c->plan.reject_fadeoff; out[27] = c->plan.intensity;
     return MEAO_OK;
 }
@@ -1084,7 +1191,12 @@ void meao_render_event(int event_id)
 MeaoRenderEventFunc meao_get_render_event_func(void) { return meao_render_event; }
 
 int64_t meao_launch_count(const MeaoCtx *c) { return c ? c->launches : 0; }
-int meao_kernels_per_frame(const MeaoCtx *) { return 9; }
+int meao_kernels_per_frame(const MeaoCtx *c)
+{
+    int n = 9;
+    if (c) for (int k = 1; k <= 4; k++) n += hq_level(c, k) ? 1 : 0;
+    return n;
+}
 
 int64_t meao_algorithmic_bytes(const MeaoCtx *c, int32_t stage)
 {

@@ -18,6 +18,13 @@
 // clamp/padding per texel with a gather from global memory.
 //
 // Bound: instruction issue (about 250 thread-instructions per output, 2 B + 1 B of HBM traffic).
+//
+// Variants (shipped in Render.compute but never dispatched by AmbientOcclusion.cs):
+//   MODE 1 = kernel `main` (WIDE_SAMPLING, REN:27-29,46-50,79-82,115-116,125,136,174): plain f32 Texture2D
+//            source (LowDepth<k> itself, no f16 rounding, no atlas), taps at 2x the offsets, per-texel
+//            clamp-to-edge in level space, output at the same resolution -> HighQuality<k>.  Same CTA
+//            shape; the apron shrinks to 8 texels (TMA box 80 x 48) and the tap stride to 2.
+//   EXH      = #define SAMPLE_EXHAUSTIVELY (REN:144-159): twelve TestSamples calls (68 taps) instead of seven (36).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -32,16 +39,21 @@ namespace {
 #define MEAO_REN_THREADS 256
 #endif
 constexpr int kTW = 64, kTH = MEAO_REN_TH;  // outputs per CTA (64x32 / 256 threads measured 2 % faster than 64x16 / 128 in the 3-stream frame pipeline)
-constexpr int kAp = 16;                     // apron: 4 slice texels x stride 4
-constexpr int kSW = kTW + 2 * kAp;          // 96  == kRenderBoxW
-constexpr int kSH = kTH + 2 * kAp;          // 64  == kRenderBoxH
+// MODE 0 (main_interleaved): apron 4 slice texels x stride 4 = 16; MODE 1 (main, wide): apron 4 taps x stride 2 = 8
+template <int MODE> struct Geo {
+    static constexpr int kStride = MODE == 0 ? 4 : 2;
+    static constexpr int kAp = MODE == 0 ? 16 : 8;
+    static constexpr int kSW = kTW + 2 * kAp;       // 96 == kRenderBoxW      | 80 == kRenderWideBoxW
+    static constexpr int kSH = kTH + 2 * kAp;       // 64 == kRenderBoxH      | 48 == kRenderWideBoxH
+};
 #ifndef MEAO_REN_MINB
 #define MEAO_REN_MINB 4
 #endif
 constexpr int kThreads = MEAO_REN_THREADS;
 constexpr int kWarps = kThreads / 32;
-static_assert((kSW * kSH / 4) % kThreads == 0, "tile must split evenly over the threads");
-static_assert(kSW == kRenderBoxW && kSH == kRenderBoxH, "TMA box mismatch");
+static_assert((Geo<0>::kSW * Geo<0>::kSH / 4) % kThreads == 0, "tile must split evenly over the threads");
+static_assert(Geo<0>::kSW == kRenderBoxW && Geo<0>::kSH == kRenderBoxH, "TMA box mismatch");
+static_assert(Geo<1>::kSW == kRenderWideBoxW && Geo<1>::kSH == kRenderWideBoxH, "TMA box mismatch (wide)");
 static_assert(kTH % kWarps == 0, "rows must split evenly over the warps");
 
 // Render.compute:60-75 for one sample pair, TWO horizontally adjacent pixels at once (.x / .y lanes).
@@ -76,50 +88,52 @@ __device__ __forceinline__ float2 pair_eval2(float2 S1, float2 S2, float2 inv_ra
 }
 
 // c points at the (left) centre texel in the smem tile
-template <int DX, int DY>
+template <int MODE, int DX, int DY>
 __device__ __forceinline__ float2 pair2(const float *c, float2 ir, float2 nf, float rf)
 {
-    constexpr int OFF = (4 * DY) * kSW + 4 * DX;
+    constexpr int OFF = (Geo<MODE>::kStride * DY) * Geo<MODE>::kSW + Geo<MODE>::kStride * DX;
     const float2 s1 = *reinterpret_cast<const float2 *>(c + OFF);
     const float2 s2 = *reinterpret_cast<const float2 *>(c - OFF);
     return pair_eval2(s1, s2, ir, nf, rf);
 }
 
 // Render.compute:87-93 (axial), x = N
-template <int N>
+template <int MODE, int N>
 __device__ __forceinline__ void axial2(const float *c, float2 inv, float it, float nfs, float w, float rf, float2 &ao)
 {
     const float2 ir = __fmul2_rn(make_float2(it, it), inv), nf = make_float2(nfs, nfs);      // REN:84
-    const float2 a = pair2<N, 0>(c, ir, nf, rf);
-    const float2 b = pair2<0, N>(c, ir, nf, rf);
+    const float2 a = pair2<MODE, N, 0>(c, ir, nf, rf);
+    const float2 b = pair2<MODE, 0, N>(c, ir, nf, rf);
     ao = __ffma2_rn(make_float2(w, w), __fmul2_rn(make_float2(0.5f, 0.5f), __fadd2_rn(a, b)), ao);
 }
 // Render.compute:94-100 (diagonal), x == y == N: offsets x*TILE - x, x*TILE + x
-template <int N>
+template <int MODE, int N>
 __device__ __forceinline__ void diag2(const float *c, float2 inv, float it, float nfs, float w, float rf, float2 &ao)
 {
     const float2 ir = __fmul2_rn(make_float2(it, it), inv), nf = make_float2(nfs, nfs);
-    const float2 a = pair2<-N, N>(c, ir, nf, rf);
-    const float2 b = pair2<N, N>(c, ir, nf, rf);
+    const float2 a = pair2<MODE, -N, N>(c, ir, nf, rf);
+    const float2 b = pair2<MODE, N, N>(c, ir, nf, rf);
     ao = __ffma2_rn(make_float2(w, w), __fmul2_rn(make_float2(0.5f, 0.5f), __fadd2_rn(a, b)), ao);
 }
 // Render.compute:101-109 (L-shaped): y*T + x, y*T - x, x*T + y, x*T - y
-template <int X, int Y>
+template <int MODE, int X, int Y>
 __device__ __forceinline__ void lshape2(const float *c, float2 inv, float it, float nfs, float w, float rf, float2 &ao)
 {
     const float2 ir = __fmul2_rn(make_float2(it, it), inv), nf = make_float2(nfs, nfs);
-    const float2 a = pair2<X, Y>(c, ir, nf, rf);
-    const float2 b = pair2<-X, Y>(c, ir, nf, rf);
-    const float2 cc = pair2<Y, X>(c, ir, nf, rf);
-    const float2 d = pair2<-Y, X>(c, ir, nf, rf);
+    const float2 a = pair2<MODE, X, Y>(c, ir, nf, rf);
+    const float2 b = pair2<MODE, -X, Y>(c, ir, nf, rf);
+    const float2 cc = pair2<MODE, Y, X>(c, ir, nf, rf);
+    const float2 d = pair2<MODE, -Y, X>(c, ir, nf, rf);
     const float2 t = __fadd2_rn(__fadd2_rn(__fadd2_rn(a, b), cc), d);
     ao = __ffma2_rn(make_float2(w, w), __fmul2_rn(make_float2(0.25f, 0.25f), t), ao);
 }
 
+template <int MODE, bool EXH>
 __global__ void __launch_bounds__(kThreads, MEAO_REN_MINB)
 render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a, const int use_tma)
 {
 #ifdef MEAO_DEVICE_OK
+    constexpr int kAp = Geo<MODE>::kAp, kSW = Geo<MODE>::kSW, kSH = Geo<MODE>::kSH;
     extern __shared__ __align__(128) float tile[];     // kSW * kSH floats
     __shared__ __align__(8) uint64_t bar;
 
@@ -130,7 +144,7 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
     const bool interior = use_tma && (X0 - kAp >= 0) && (Y0 - kAp >= 0) && (X0 + kTW + kAp <= a.lw) && (Y0 + kTH + kAp <= a.lh);
 
     if (interior) {
-        // ---- TMA: one 96x64 f32 box, completion on an mbarrier --------------------------------
+        // ---- TMA: one 96x64 (wide: 80x48) f32 box, completion on an mbarrier ------------------
         if (tid == 0) {
             mbar_init(&bar, 1);
             fence_mbar_init();
@@ -141,13 +155,22 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
             tma_load_2d(tile, &low_map, X0 - kAp, Y0 - kAp, &bar);
         }
         mbar_wait(&bar, 0);
-        // in-place f16 rounding (what the RHalf atlas store of DS1:71 / DS2:41 does)
-        float4 *t4 = reinterpret_cast<float4 *>(tile);
+        if (MODE == 0) {
+            // in-place f16 rounding (what the RHalf atlas store of DS1:71 / DS2:41 does)
+            float4 *t4 = reinterpret_cast<float4 *>(tile);
 #pragma unroll
-        for (int i = 0; i < (kSW * kSH / 4) / kThreads; i++) {
-            float4 q = t4[tid + i * kThreads];
-            q.x = f16_round(q.x); q.y = f16_round(q.y); q.z = f16_round(q.z); q.w = f16_round(q.w);
-            t4[tid + i * kThreads] = q;
+            for (int i = 0; i < (kSW * kSH / 4) / kThreads; i++) {
+                float4 q = t4[tid + i * kThreads];
+                q.x = f16_round(q.x); q.y = f16_round(q.y); q.z = f16_round(q.z); q.w = f16_round(q.w);
+                t4[tid + i * kThreads] = q;
+            }
+        }
+    } else if (MODE == 1) {
+        // ---- border tile, kernel `main`: per-texel clamp-to-edge of the Gather (REN:125), f32 as stored ----
+        for (int idx = tid; idx < kSW * kSH; idx += kThreads) {
+            const int tx = idx % kSW, ty = idx / kSW;
+            const int sx = iclamp(X0 - kAp + tx, 0, a.lw - 1), sy = iclamp(Y0 - kAp + ty, 0, a.lh - 1);
+            tile[idx] = __ldg(a.low + (size_t)sy * a.lpitch + sx);
         }
     } else {
         // ---- border tile: resolve slice-space clamp + atlas padding per texel ------------------
@@ -176,14 +199,30 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
         const float2 ctr = *reinterpret_cast<const float2 *>(c);
         const float2 inv = make_float2(rcp_ieee(ctr.x), rcp_ieee(ctr.y));      // REN:140
         float2 ao = make_float2(0.0f, 0.0f);                                   // REN:142
-        // REN:162-168 -- the 36-sample checker pattern, in call order
-        axial2<2>(c, inv, a.inv_thickness[0], a.neg_front[0], a.weight[0], rf, ao);
-        axial2<4>(c, inv, a.inv_thickness[1], a.neg_front[1], a.weight[1], rf, ao);
-        diag2<1>(c, inv, a.inv_thickness[2], a.neg_front[2], a.weight[2], rf, ao);
-        diag2<2>(c, inv, a.inv_thickness[3], a.neg_front[3], a.weight[3], rf, ao);
-        diag2<3>(c, inv, a.inv_thickness[4], a.neg_front[4], a.weight[4], rf, ao);
-        lshape2<1, 3>(c, inv, a.inv_thickness[5], a.neg_front[5], a.weight[5], rf, ao);
-        lshape2<2, 4>(c, inv, a.inv_thickness[6], a.neg_front[6], a.weight[6], rf, ao);
+        if (!EXH) {
+            // REN:162-168 -- the 36-sample checker pattern, in call order
+            axial2<MODE, 2>(c, inv, a.inv_thickness[0], a.neg_front[0], a.weight[0], rf, ao);
+            axial2<MODE, 4>(c, inv, a.inv_thickness[1], a.neg_front[1], a.weight[1], rf, ao);
+            diag2<MODE, 1>(c, inv, a.inv_thickness[2], a.neg_front[2], a.weight[2], rf, ao);
+            diag2<MODE, 2>(c, inv, a.inv_thickness[3], a.neg_front[3], a.weight[3], rf, ao);
+            diag2<MODE, 3>(c, inv, a.inv_thickness[4], a.neg_front[4], a.weight[4], rf, ao);
+            lshape2<MODE, 1, 3>(c, inv, a.inv_thickness[5], a.neg_front[5], a.weight[5], rf, ao);
+            lshape2<MODE, 2, 4>(c, inv, a.inv_thickness[6], a.neg_front[6], a.weight[6], rf, ao);
+        } else {
+            // REN:148-159 -- SAMPLE_EXHAUSTIVELY: all 68 cells within radius 5, in call order
+            axial2<MODE, 1>(c, inv, a.inv_thickness[0], a.neg_front[0], a.weight[0], rf, ao);
+            axial2<MODE, 2>(c, inv, a.inv_thickness[1], a.neg_front[1], a.weight[1], rf, ao);
+            axial2<MODE, 3>(c, inv, a.inv_thickness[2], a.neg_front[2], a.weight[2], rf, ao);
+            axial2<MODE, 4>(c, inv, a.inv_thickness[3], a.neg_front[3], a.weight[3], rf, ao);
+            diag2<MODE, 1>(c, inv, a.inv_thickness[4], a.neg_front[4], a.weight[4], rf, ao);
+            diag2<MODE, 2>(c, inv, a.inv_thickness[5], a.neg_front[5], a.weight[5], rf, ao);
+            diag2<MODE, 3>(c, inv, a.inv_thickness[6], a.neg_front[6], a.weight[6], rf, ao);
+            lshape2<MODE, 1, 2>(c, inv, a.inv_thickness[7], a.neg_front[7], a.weight[7], rf, ao);
+            lshape2<MODE, 1, 3>(c, inv, a.inv_thickness[8], a.neg_front[8], a.weight[8], rf, ao);
+            lshape2<MODE, 1, 4>(c, inv, a.inv_thickness[9], a.neg_front[9], a.weight[9], rf, ao);
+            lshape2<MODE, 2, 3>(c, inv, a.inv_thickness[10], a.neg_front[10], a.weight[10], rf, ao);
+            lshape2<MODE, 2, 4>(c, inv, a.inv_thickness[11], a.neg_front[11], a.weight[11], rf, ao);
+        }
         // REN:176  lerp(1, ao, gIntensity) -> R8
         const float2 le = __ffma2_rn(make_float2(a.intensity, a.intensity), __fadd2_rn(ao, make_float2(-1.0f, -1.0f)), make_float2(1.0f, 1.0f));
         const uint32_t k0 = unorm8_code(le.x);
@@ -213,8 +252,16 @@ cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const Ren
     if (a.row1 <= a.row0) return cudaSuccess;
     const int ybase = a.row0 & ~3;
     dim3 grid(ceil_div(a.lw, kTW), ceil_div(a.row1 - ybase, kTH));
-    const size_t smem = (size_t)kSW * kSH * sizeof(float);
-    render_ao_kernel<<<grid, kThreads, smem, s>>>(low_map, a, use_tma ? 1 : 0);
+    const int t = use_tma ? 1 : 0;
+    if (!a.wide) {
+        const size_t smem = (size_t)Geo<0>::kSW * Geo<0>::kSH * sizeof(float);
+        if (!a.exhaustive) render_ao_kernel<0, false><<<grid, kThreads, smem, s>>>(low_map, a, t);
+        else               render_ao_kernel<0, true><<<grid, kThreads, smem, s>>>(low_map, a, t);
+    } else {
+        const size_t smem = (size_t)Geo<1>::kSW * Geo<1>::kSH * sizeof(float);
+        if (!a.exhaustive) render_ao_kernel<1, false><<<grid, kThreads, smem, s>>>(low_map, a, t);
+        else               render_ao_kernel<1, true><<<grid, kThreads, smem, s>>>(low_map, a, t);
+    }
     return cudaGetLastError();
 }
 

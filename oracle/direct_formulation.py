@@ -66,9 +66,15 @@ def tiled_view(low_k, sw, sh, pad):
     return _f16r(out)
 
 
-def render_ao(low_k, sw, sh, pad, consts):
-    """Occlusion<k> codes.  Pixel (X,Y): slice (X&3,Y&3), slice texel (X>>2,Y>>2); tap (di,dj) reads
-    natural pixel (4*clamp(i+di)+sx, 4*clamp(j+dj)+sy), `pad` when outside the level."""
+# (table slot, (x, y)) in call order
+SAMPLES_CHECKER = ((1, (2, 0)), (3, (4, 0)), (4, (1, 1)), (8, (2, 2)), (11, (3, 3)), (6, (1, 3)), (10, (2, 4)))     # REN:162-168
+SAMPLES_EXHAUSTIVE = ((0, (1, 0)), (1, (2, 0)), (2, (3, 0)), (3, (4, 0)), (4, (1, 1)), (8, (2, 2)), (11, (3, 3)),
+                      (5, (1, 2)), (6, (1, 3)), (7, (1, 4)), (9, (2, 3)), (10, (2, 4)))                             # REN:148-159
+
+
+def render_ao(low_k, sw, sh, pad, consts, exhaustive=False):
+    """Occlusion<k> codes (kernel main_interleaved).  Pixel (X,Y): slice (X&3,Y&3), slice texel (X>>2,Y>>2); tap (di,dj)
+    reads natural pixel (4*clamp(i+di)+sx, 4*clamp(j+dj)+sy), `pad` when outside the level."""
     lh, lw = low_k.shape
     lowh = _f16r(low_k)
     padh = _f16r(np.asarray(pad, F))
@@ -81,6 +87,23 @@ def render_ao(low_k, sw, sh, pad, consts):
         ok = (cx < lw) & (cy < lh)
         return np.where(ok, lowh[np.minimum(cy, lh - 1), np.minimum(cx, lw - 1)], padh).astype(F)
 
+    return _render_core(tap, (lh, lw), consts, exhaustive)
+
+
+def render_ao_wide(low_k, consts, exhaustive=False):
+    """HighQuality<k> codes (kernel main, WIDE_SAMPLING): f32 source sampled in place, tap (di,dj) reads level pixel
+    (clamp(X + 2*di), clamp(Y + 2*dj)) -- REN:79-82 doubles the offsets, REN:125 clamps per texel."""
+    lh, lw = low_k.shape
+    Y, X = np.meshgrid(np.arange(lh), np.arange(lw), indexing="ij")
+
+    def tap(di, dj):
+        return low_k[np.clip(Y + 2 * dj, 0, lh - 1), np.clip(X + 2 * di, 0, lw - 1)].astype(F)
+
+    return _render_core(tap, (lh, lw), consts, exhaustive)
+
+
+def _render_core(tap, shape, consts, exhaustive):
+    lh, lw = shape
     rf = F(consts["reject_fadeoff"])
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         inv_depth = (F(1) / tap(0, 0)).astype(F)                                # REN:140
@@ -105,7 +128,7 @@ def render_ao(low_k, sw, sh, pad, consts):
 
         iT, sW = consts["inv_thickness"], consts["sample_weight"]
         ao = np.zeros((lh, lw), F)
-        for idx, (x, y) in ((1, (2, 0)), (3, (4, 0)), (4, (1, 1)), (8, (2, 2)), (11, (3, 3)), (6, (1, 3)), (10, (2, 4))):   # REN:162-168
+        for idx, (x, y) in (SAMPLES_EXHAUSTIVE if exhaustive else SAMPLES_CHECKER):
             ao = (F(sW[idx]) * samples(x, y, iT[idx]) + ao).astype(F)
         out = (F(consts["intensity"]) * (ao - F(1)) + F(1)).astype(F)           # REN:176
     return _unorm8(out)
@@ -131,8 +154,11 @@ def _blur_1d(ao5, id5, step, kblur):
     return _smart_blur(ao5[0], ao5[1], ao5[2], ao5[3], ao5[4], cc[0], cc[1], cc[2])
 
 
-def blur_upsample(lo_depth, lo_ao_codes, hi_depth, hi_ao_codes, consts):
-    """AoResult codes at the hi level.  hi_ao_codes None => kernel "main" (UPS:223)."""
+def blur_upsample(lo_depth, lo_ao_codes, hi_depth, hi_ao_codes, consts, lo_ao2_codes=None):
+    """AoResult codes at the hi level.  hi_ao_codes None => kernel "main" (UPS:223); lo_ao2_codes given => the
+    main_premin variants: AO1 = min(AO1, LoResAO2) per texel before the blur (UPS:58-60)."""
+    if lo_ao2_codes is not None:
+        lo_ao_codes = np.minimum(lo_ao_codes, lo_ao2_codes)      # k -> k/255 is monotone, so min commutes with the load
     loh, low = lo_depth.shape
     hih, hiw = hi_depth.shape
     step, kblur = F(consts["step_size"]), F(consts["blur_tolerance"])
@@ -191,7 +217,8 @@ def blur_upsample(lo_depth, lo_ao_codes, hi_depth, hi_ao_codes, consts):
     return _unorm8(res)
 
 
-def run(depth, render_consts, upsample_consts, zb, *, reversed_z=True, linear=False, return_all=False):
+def run(depth, render_consts, upsample_consts, zb, *, reversed_z=True, linear=False, return_all=False,
+        exhaustive=False, high_quality_mask=0, render_consts_wide=None):
     """Whole pipe (AO.cs:511-531).  render_consts / upsample_consts: dicts per level from the oracle."""
     H, W = depth.shape
     dims = level_dims(W, H)
@@ -203,15 +230,35 @@ def run(depth, render_consts, upsample_consts, zb, *, reversed_z=True, linear=Fa
     occ = [None] * 5
     for k in range(1, 5):
         sw, sh = dims[k + 2]
-        occ[k] = render_ao(low[k], sw, sh, pad12 if k <= 2 else F(0), render_consts[k])
+        occ[k] = render_ao(low[k], sw, sh, pad12 if k <= 2 else F(0), render_consts[k], exhaustive)
+    hq = [None] * 5
+    for k in range(1, 5):
+        if (high_quality_mask >> (k - 1)) & 1:
+            hq[k] = render_ao_wide(low[k], render_consts_wide[k], exhaustive)
     comb = [None] * 4
     lo_ao = occ[4]
     for lo in range(4, 0, -1):
         hi = lo - 1
         hi_depth = lin_h if hi == 0 else low[hi]
         hi_ao = None if hi == 0 else occ[hi]
-        comb[hi] = blur_upsample(low[lo], lo_ao, hi_depth, hi_ao, upsample_consts[lo])
+        comb[hi] = blur_upsample(low[lo], lo_ao, hi_depth, hi_ao, upsample_consts[lo], hq[lo])
         lo_ao = comb[hi]
     if return_all:
-        return {"linear": lin_h, "low": low, "occ": occ, "comb": comb, "pad12": pad12}
+        return {"linear": lin_h, "low": low, "occ": occ, "comb": comb, "pad12": pad12, "hq": hq}
     return comb[0]
+
+
+def debug_view(buf, W, H):
+    """PushDebugBlitCommands (AO.cs:787-820): the W x H R8 image of a buffer.  buf: [h, w] (stretch blit, point sampling at
+    the pixel centre) or [16, h, w] (Blit.shader pass 4 :150-152: a 4 x 4 mosaic of the slices).  Values, not codes."""
+    y, x = np.arange(H, dtype=np.int64), np.arange(W, dtype=np.int64)
+    if buf.ndim == 3:
+        _, sh, sw = buf.shape
+        nx, ny = 8 * x + 4, 8 * y + 4
+        qx, qy = nx // (2 * W), ny // (2 * H)
+        tx, ty = (nx - 2 * W * qx) * sw // (2 * W), (ny - 2 * H * qy) * sh // (2 * H)
+        v = buf[(qx[None, :] + 4 * qy[:, None]), ty[:, None], tx[None, :]]
+    else:
+        sh, sw = buf.shape
+        v = buf[((2 * y + 1) * sh // (2 * H))[:, None], ((2 * x + 1) * sw // (2 * W))[None, :]]
+    return _unorm8(v.astype(F))

@@ -114,6 +114,7 @@ MeaoOracle *meao_oracle_create(int width, int height)
         o->tiled_depth[k] = ALLOC((size_t)16 * o->lw[k + 2] * o->lh[k + 2]);
         o->occlusion[k] = ALLOC((size_t)o->lw[k] * o->lh[k]);
         if (k <= 3) o->combined[k] = ALLOC((size_t)o->lw[k] * o->lh[k]);
+        o->high_quality[k] = ALLOC((size_t)o->lw[k] * o->lh[k]);
     }
     o->result = ALLOC((size_t)o->lw[0] * o->lh[0]);
 #undef ALLOC
@@ -125,7 +126,7 @@ void meao_oracle_destroy(MeaoOracle *o)
     if (!o) return;
     free(o->linear_depth); free(o->result);
     for (int k = 1; k <= 4; k++) {
-        free(o->low_depth[k]); free(o->tiled_depth[k]); free(o->occlusion[k]);
+        free(o->low_depth[k]); free(o->tiled_depth[k]); free(o->occlusion[k]); free(o->high_quality[k]);
         if (k <= 3) free(o->combined[k]);
     }
     free(o);
@@ -140,6 +141,7 @@ float *meao_oracle_buffer_mut(MeaoOracle *o, int id, int *w, int *h, int *slices
     else if (id >= 10 && id <= 13) { lvl = id - 9; p = o->occlusion[id - 9]; }
     else if (id >= 14 && id <= 16) { lvl = id - 13; p = o->combined[id - 13]; }
     else if (id == 17) { lvl = 0; p = o->result; }
+    else if (id >= 18 && id <= 21) { lvl = id - 17; p = o->high_quality[id - 17]; }   /* extension: HighQuality1..4 */
     else return NULL;
     if (w) *w = o->lw[lvl];
     if (h) *h = o->lh[lvl];
@@ -185,23 +187,25 @@ void meao_oracle_sample_thickness(float t[12])
     t[11] = mathf_sqrt(1 - 0.6f * 0.6f - 0.6f * 0.6f);
 }
 
-/* AmbientOcclusion.cs:660-734 (source = TiledDepth<level>, i.e. mip level+2, always tiled) */
-void meao_oracle_render_constants(const MeaoOracle *o, int level,
+/* AmbientOcclusion.cs:660-734 for a source of src_w x src_h texels; tiled: source.isTiled (AO.cs:679) */
+static void render_constants_impl(const MeaoOracle *o, int src_w, int src_h, int tiled,
                                   float inv_thickness[12], float sample_weight[12],
                                   float inv_slice_dim[2], float *reject_fadeoff, float *intensity)
 {
     float thick[12];
     meao_oracle_sample_thickness(thick);
     const float ScreenspaceDiameter = 10;                                   /* AO.cs:669 */
-    int src_w = o->lw[level + 2], src_h = o->lh[level + 2];
     float ThicknessMultiplier = 2 * o->camera.tan_half_fov_h * ScreenspaceDiameter / (float)src_w; /* AO.cs:678 */
-    /* AO.cs:679 (!isTiled) and :680 (single-pass stereo) never apply on this path */
+    if (!tiled) ThicknessMultiplier *= 2;                                   /* AO.cs:679 */
+    if (o->single_pass_stereo) ThicknessMultiplier *= 2;                    /* AO.cs:680 */
     float InverseRangeFactor = 1 / ThicknessMultiplier;                     /* AO.cs:683 */
     for (int i = 0; i < 12; i++) inv_thickness[i] = InverseRangeFactor / thick[i];   /* AO.cs:687-688 */
     static const float mult[12] = {4, 4, 4, 4, 4, 8, 8, 8, 4, 8, 8, 4};     /* AO.cs:696-707 */
     for (int i = 0; i < 12; i++) sample_weight[i] = mult[i] * thick[i];
-    sample_weight[0] = 0; sample_weight[2] = 0; sample_weight[5] = 0;       /* AO.cs:711-715 */
-    sample_weight[7] = 0; sample_weight[9] = 0;
+    if (!o->sample_exhaustively) {                                          /* AO.cs:709-715 ("FIXME: should we support SAMPLE_EXHAUSTIVELY mode?") */
+        sample_weight[0] = 0; sample_weight[2] = 0; sample_weight[5] = 0;
+        sample_weight[7] = 0; sample_weight[9] = 0;
+    }
     float total = 0.0f;                                                     /* AO.cs:718-724 */
     for (int i = 0; i < 12; i++) total += sample_weight[i];
     for (int i = 0; i < 12; i++) sample_weight[i] /= total;
@@ -209,6 +213,22 @@ void meao_oracle_render_constants(const MeaoOracle *o, int level,
     inv_slice_dim[1] = 1.0f / (float)src_h;
     *reject_fadeoff = -1 / o->params.thickness_modifier;                    /* AO.cs:733 */
     *intensity = o->params.intensity;                                       /* AO.cs:734 */
+}
+
+/* source = TiledDepth<level>, i.e. mip level+2, tiled (the only calls AmbientOcclusion.cs makes, AO.cs:519-522) */
+void meao_oracle_render_constants(const MeaoOracle *o, int level,
+                                  float inv_thickness[12], float sample_weight[12],
+                                  float inv_slice_dim[2], float *reject_fadeoff, float *intensity)
+{
+    render_constants_impl(o, o->lw[level + 2], o->lh[level + 2], 1, inv_thickness, sample_weight, inv_slice_dim, reject_fadeoff, intensity);
+}
+
+/* source = LowDepth<level>, not tiled (kernel "main"; PushRenderCommands would take the AO.cs:679 branch) */
+void meao_oracle_render_constants_wide(const MeaoOracle *o, int level,
+                                       float inv_thickness[12], float sample_weight[12],
+                                       float inv_slice_dim[2], float *reject_fadeoff, float *intensity)
+{
+    render_constants_impl(o, o->lw[level], o->lh[level], 0, inv_thickness, sample_weight, inv_slice_dim, reject_fadeoff, intensity);
 }
 
 /* AmbientOcclusion.cs:757-771 */
@@ -371,14 +391,17 @@ static inline float4_t gather4(const float *buf, int w, int h, int cx, int cy)
 }
 
 /* ------------------------------------------------------------------------------------------
- * Render.compute, kernel main_interleaved (INTERLEAVE_RESULT => TILE_DIM 16, 8x8 threads)
+ * Render.compute: kernel main_interleaved (INTERLEAVE_RESULT => TILE_DIM 16, 8x8 threads, 16-slice
+ * Texture2DArray source) and kernel main (WIDE_SAMPLING => TILE_DIM 32, 16x16 threads, plain
+ * Texture2D source).  SAMPLE_EXHAUSTIVELY (REN:144-159) is a compile-time switch of both.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     MeaoOracle *o; int level;
     float inv_thickness[12], sample_weight[12], inv_slice_dim[2], reject_fadeoff, intensity;
 } ren_ctx;
 
-#define REN_TILE_DIM 16
+#define REN_TILE_DIM 16        /* REN:53 */
+#define REN_TILE_DIM_WIDE 32   /* REN:48 */
 
 /* Render.compute:60-75 */
 static inline float ren_test_sample_pair(const float *DS, float rf, float frontDepth, float invRange, unsigned base, int offset)
@@ -391,26 +414,48 @@ static inline float ren_test_sample_pair(const float *DS, float rf, float frontD
     return sat(mad(-pseudo1, pseudo2, s));                                        /* REN:71-74 */
 }
 
-/* Render.compute:77-110 */
-static inline float ren_test_samples(const float *DS, float rf, unsigned centerIdx, unsigned x, unsigned y, float invDepth, float invThickness)
+/* Render.compute:77-110; T = TILE_DIM, wide = WIDE_SAMPLING */
+static inline float ren_test_samples(const float *DS, float rf, unsigned T, int wide, unsigned centerIdx, unsigned x, unsigned y, float invDepth, float invThickness)
 {
+    if (wide) { x <<= 1; y <<= 1; }                                               /* REN:79-82 */
     float invRange = invThickness * invDepth;                                     /* REN:84 */
     float frontDepth = invThickness - 0.5f;                                       /* REN:85 */
     if (y == 0) {                                                                 /* REN:87-93 axial */
         return 0.5f * (ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)x) +
-                       ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * REN_TILE_DIM)));
+                       ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * T)));
     } else if (x == y) {                                                          /* REN:94-100 diagonal */
-        return 0.5f * (ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * REN_TILE_DIM - x)) +
-                       ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * REN_TILE_DIM + x)));
+        return 0.5f * (ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * T - x)) +
+                       ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * T + x)));
     } else {                                                                      /* REN:101-109 L-shaped */
-        return 0.25f * (ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(y * REN_TILE_DIM + x)) +
-                        ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(y * REN_TILE_DIM - x)) +
-                        ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * REN_TILE_DIM + y)) +
-                        ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * REN_TILE_DIM - y)));
+        return 0.25f * (ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(y * T + x)) +
+                        ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(y * T - x)) +
+                        ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * T + y)) +
+                        ren_test_sample_pair(DS, rf, frontDepth, invRange, centerIdx, (int)(x * T - y)));
     }
 }
 
-/* Render.compute:112-177; dispatch ceil(w/8) x ceil(h/8) x 16, AO.cs:739-747.
+/* Render.compute:142-169: the weighted sum over the sample set.  Table slots: float4[3] arrays indexed [i/4][i%4] (REN:39-40). */
+static inline float ren_accumulate(const ren_ctx *c, const float *DS, unsigned T, int wide, unsigned thisIdx, float invThisDepth)
+{
+    const float *iT = c->inv_thickness, *sW = c->sample_weight;
+    const float rf = c->reject_fadeoff;
+    float ao = 0.0f;                                                              /* REN:142 */
+#define TS(slot, x, y) ao = mad(sW[slot], ren_test_samples(DS, rf, T, wide, thisIdx, x, y, invThisDepth, iT[slot]), ao)
+    if (c->o->sample_exhaustively) {
+        /* REN:146-159, 68 samples: all cells within a circular radius of 5 */
+        TS(0, 1, 0); TS(1, 2, 0); TS(2, 3, 0); TS(3, 4, 0);                       /* REN:148-151  [0].xyzw */
+        TS(4, 1, 1); TS(8, 2, 2); TS(11, 3, 3);                                   /* REN:152-154  [1].x [2].x [2].w */
+        TS(5, 1, 2); TS(6, 1, 3); TS(7, 1, 4);                                    /* REN:155-157  [1].yzw */
+        TS(9, 2, 3); TS(10, 2, 4);                                                /* REN:158-159  [2].yz */
+    } else {
+        /* REN:162-168, 36-sample checker pattern */
+        TS(1, 2, 0); TS(3, 4, 0); TS(4, 1, 1); TS(8, 2, 2); TS(11, 3, 3); TS(6, 1, 3); TS(10, 2, 4);
+    }
+#undef TS
+    return ao;
+}
+
+/* Render.compute:112-177 as main_interleaved; dispatch ceil(w/8) x ceil(h/8) x 16, AO.cs:739-747.
  * Stripes run over (slice z, group row gy) pairs flattened as z * ngy + gy. */
 static void ren_stripe(void *vc, int r0, int r1)
 {
@@ -419,8 +464,6 @@ static void ren_stripe(void *vc, int r0, int r1)
     const int sw = o->lw[k + 2], sh = o->lh[k + 2];
     const int ow = o->lw[k], oh = o->lh[k];
     const int ngx = (sw + 7) / 8, ngy = (sh + 7) / 8;
-    const float *iT = c->inv_thickness, *sW = c->sample_weight;   /* float4[3] slots [i/4][i%4], REN:39-40 */
-    const float rf = c->reject_fadeoff;
     float DS[REN_TILE_DIM * REN_TILE_DIM];                        /* REN:58 */
     for (int r = r0; r < r1; r++) {
         int z = r / ngy, gy = r % ngy;
@@ -437,15 +480,7 @@ static void ren_stripe(void *vc, int r0, int r1)
             for (int ty = 0; ty < 8; ty++) for (int tx = 0; tx < 8; tx++) {
                 unsigned thisIdx = (unsigned)(tx + ty * REN_TILE_DIM + 4 * REN_TILE_DIM + 4);   /* REN:138 */
                 const float invThisDepth = 1.0f / DS[thisIdx];                                   /* REN:140 */
-                float ao = 0.0f;                                                                 /* REN:142 */
-                /* REN:162-168, 36-sample checker pattern */
-                ao = mad(sW[1],  ren_test_samples(DS, rf, thisIdx, 2, 0, invThisDepth, iT[1]),  ao);
-                ao = mad(sW[3],  ren_test_samples(DS, rf, thisIdx, 4, 0, invThisDepth, iT[3]),  ao);
-                ao = mad(sW[4],  ren_test_samples(DS, rf, thisIdx, 1, 1, invThisDepth, iT[4]),  ao);
-                ao = mad(sW[8],  ren_test_samples(DS, rf, thisIdx, 2, 2, invThisDepth, iT[8]),  ao);
-                ao = mad(sW[11], ren_test_samples(DS, rf, thisIdx, 3, 3, invThisDepth, iT[11]), ao);
-                ao = mad(sW[6],  ren_test_samples(DS, rf, thisIdx, 1, 3, invThisDepth, iT[6]),  ao);
-                ao = mad(sW[10], ren_test_samples(DS, rf, thisIdx, 2, 4, invThisDepth, iT[10]), ao);
+                float ao = ren_accumulate(c, DS, REN_TILE_DIM, 0, thisIdx, invThisDepth);        /* REN:142-169 */
                 int ox = ((gx * 8 + tx) << 2) | (z & 3), oy = ((gy * 8 + ty) << 2) | (z >> 2); /* REN:172 */
                 if (ox < ow && oy < oh)
                     o->occlusion[k][(size_t)oy * ow + ox] = st_unorm8(o, mad(c->intensity, ao - 1.0f, 1.0f)); /* REN:176 lerp(1, ao, I) */
@@ -463,12 +498,51 @@ void meao_oracle_render(MeaoOracle *o, int level, int threads)
     run_striped(ren_stripe, &c, 16 * ngy, threads);
 }
 
+/* Render.compute:112-177 as kernel "main": WIDE_SAMPLING, TILE_DIM 32, 16x16 threads (REN:46-50), source =
+ * Texture2D<float> LowDepth<level> (f32, point + clamp Gather REN:125), output at DTid.xy (REN:174).
+ * Dispatch by the generic formula of AO.cs:742-747 with the kernel's own group size: ceil(w/16) x ceil(h/16) x 1. */
+static void ren_wide_stripe(void *vc, int gy0, int gy1)
+{
+    ren_ctx *c = (ren_ctx *)vc; MeaoOracle *o = c->o;
+    const int k = c->level;
+    const int sw = o->lw[k], sh = o->lh[k];
+    const int ngx = (sw + 15) / 16;
+    const float *src = o->low_depth[k];
+    float DS[REN_TILE_DIM_WIDE * REN_TILE_DIM_WIDE];                                 /* REN:58 */
+    for (int gy = gy0; gy < gy1; gy++)
+    for (int gx = 0; gx < ngx; gx++) {
+        for (int ty = 0; ty < 16; ty++) for (int tx = 0; tx < 16; tx++) {
+            int cx = gx * 16 + tx + tx - 7, cy = gy * 16 + ty + ty - 7;              /* REN:116 (DTid + GTid - 7) * invDim */
+            float4_t d = gather4(src, sw, sh, cx, cy);                               /* REN:125 */
+            int dest = tx * 2 + ty * 2 * REN_TILE_DIM_WIDE;                          /* REN:127 */
+            DS[dest] = d.w; DS[dest + 1] = d.z;                                      /* REN:128-129 */
+            DS[dest + REN_TILE_DIM_WIDE] = d.x; DS[dest + REN_TILE_DIM_WIDE + 1] = d.y;   /* REN:130-131 */
+        }
+        /* GroupMemoryBarrierWithGroupSync REN:133 */
+        for (int ty = 0; ty < 16; ty++) for (int tx = 0; tx < 16; tx++) {
+            unsigned thisIdx = (unsigned)(tx + ty * REN_TILE_DIM_WIDE + 8 * REN_TILE_DIM_WIDE + 8);   /* REN:136 */
+            const float invThisDepth = 1.0f / DS[thisIdx];                                             /* REN:140 */
+            float ao = ren_accumulate(c, DS, REN_TILE_DIM_WIDE, 1, thisIdx, invThisDepth);             /* REN:142-169 */
+            int ox = gx * 16 + tx, oy = gy * 16 + ty;                                                  /* REN:174 */
+            if (ox < sw && oy < sh)
+                o->high_quality[k][(size_t)oy * sw + ox] = st_unorm8(o, mad(c->intensity, ao - 1.0f, 1.0f));  /* REN:176 */
+        }
+    }
+}
+
+void meao_oracle_render_wide(MeaoOracle *o, int level, int threads)
+{
+    ren_ctx c; c.o = o; c.level = level;
+    meao_oracle_render_constants_wide(o, level, c.inv_thickness, c.sample_weight, c.inv_slice_dim, &c.reject_fadeoff, &c.intensity);
+    run_striped(ren_wide_stripe, &c, (o->lh[level] + 15) / 16, threads);
+}
+
 /* ------------------------------------------------------------------------------------------
  * Upsample.compute, kernels main (no hi-res AO) and main_blendout
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     MeaoOracle *o; int lo_level;
-    const float *lo_depth, *hi_depth, *lo_ao, *hi_ao; float *dest;
+    const float *lo_depth, *hi_depth, *lo_ao, *lo_ao2, *hi_ao; float *dest;   /* lo_ao2: LoResAO2 (COMBINE_LOWER_RESOLUTIONS) or NULL */
     int low, loh, hiw, hih;
     float NoiseFilterStrength, StepSize, kBlurTolerance, kUpsampleTolerance;
 } ups_ctx;
@@ -562,6 +636,10 @@ static void ups_stripe(void *vc, int gy0, int gy1)
             unsigned index = (unsigned)((tx << 1) | (ty << 5));          /* UPS:191 */
             int cx = gx * 8 + tx + tx - 2, cy = gy * 8 + ty + ty - 2;    /* (DTid + GTid - 2) * InvLowResolution */
             float4_t A = gather4(c->lo_ao, c->low, c->loh, cx, cy);      /* UPS:56 */
+            if (c->lo_ao2) {                                             /* UPS:58-60 COMBINE_LOWER_RESOLUTIONS */
+                float4_t B = gather4(c->lo_ao2, c->low, c->loh, cx, cy);
+                A.x = hmin(A.x, B.x); A.y = hmin(A.y, B.y); A.z = hmin(A.z, B.z); A.w = hmin(A.w, B.w);
+            }
             AO1[index] = A.w; AO1[index + 1] = A.z; AO1[index + 16] = A.x; AO1[index + 17] = A.y;   /* UPS:62-65 */
             float4_t D = gather4(c->lo_depth, c->low, c->loh, cx, cy);   /* UPS:67 */
             DC[index] = 1.0f / D.w; DC[index + 1] = 1.0f / D.z; DC[index + 16] = 1.0f / D.x; DC[index + 17] = 1.0f / D.y;
@@ -598,6 +676,7 @@ void meao_oracle_upsample(MeaoOracle *o, int lo_level, int threads)
     int hi = lo_level - 1;
     c.lo_depth = o->low_depth[lo_level];
     c.lo_ao = (lo_level == 4) ? o->occlusion[4] : o->combined[lo_level];
+    c.lo_ao2 = ((o->high_quality_mask >> (lo_level - 1)) & 1) ? o->high_quality[lo_level] : NULL;   /* kernels main_premin / main_premin_blendout */
     c.hi_depth = (hi == 0) ? o->linear_depth : o->low_depth[hi];
     c.hi_ao = (hi == 0) ? NULL : o->occlusion[hi];
     c.dest = (hi == 0) ? o->result : o->combined[hi];
@@ -613,7 +692,38 @@ void meao_oracle_run(MeaoOracle *o, const float *depth, int threads)
 {
     meao_oracle_downsample(o, depth, threads);
     for (int k = 1; k <= 4; k++) meao_oracle_render(o, k, threads);
+    for (int k = 1; k <= 4; k++)                                          /* not in AO.cs: upstream's per-level high-quality pass */
+        if ((o->high_quality_mask >> (k - 1)) & 1) meao_oracle_render_wide(o, k, threads);
     for (int lo = 4; lo >= 1; lo--) meao_oracle_upsample(o, lo, threads);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Debug views: PushDebugBlitCommands (AmbientOcclusion.cs:787-820) + Blit.shader passes 3 / 4
+ * ---------------------------------------------------------------------------------------- */
+void meao_oracle_debug_view(const MeaoOracle *o, int debug_id, uint8_t *out)
+{
+    int sw, sh, slices;
+    const float *src = meao_oracle_get_buffer(o, debug_id, &sw, &sh, &slices);
+    if (!src) return;
+    const int W = o->W, H = o->H;
+    for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+        float v;
+        if (slices == 16) {
+            /* Blit.shader:150-152: uv4 = uv * 4; slice = floor(uv4.x) + floor(uv4.y) * 4; sample at frac(uv4).
+             * uv = (2x+1)/(2W): 4*uv = (8x+4)/(2W) -> integer part q, fraction r/(2W); texel = floor(frac * sw) */
+            long long nx = 8LL * x + 4, ny = 8LL * y + 4;
+            int qx = (int)(nx / (2LL * W)), qy = (int)(ny / (2LL * H));
+            long long rx = nx - 2LL * W * qx, ry = ny - 2LL * H * qy;
+            int tx = (int)(rx * sw / (2LL * W)), ty = (int)(ry * sh / (2LL * H));
+            v = src[((size_t)(qx + 4 * qy) * sh + ty) * sw + tx];
+        } else {
+            /* cmd.Blit(rt, _result) (AO.cs:817): point-sampled stretch, texel = floor(uv * size) at the pixel centre */
+            int tx = (int)((2LL * x + 1) * sw / (2LL * W)), ty = (int)((2LL * y + 1) * sh / (2LL * H));
+            v = src[(size_t)ty * sw + tx];
+        }
+        out[(size_t)y * W + x] = meao_oracle_unorm8_code(v);               /* R8 render target store (AO.cs:475) */
+    }
 }
 
 /* ------------------------------------------------------------------------------------------

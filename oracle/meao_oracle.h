@@ -17,8 +17,9 @@
  * shared arrays, barriers), one thread at a time, so every line can be checked against
  * the HLSL.  Reference files (under /root/reference/Assets/MiniEngineAO/):
  *   Shaders/Downsample1.compute:37-81, Shaders/Downsample2.compute:32-51,
- *   Shaders/Render.compute:60-177 (variant main_interleaved: INTERLEAVE_RESULT, TILE_DIM 16),
- *   Shaders/Upsample.compute:54-233 (variants main / main_blendout),
+ *   Shaders/Render.compute:60-177 (variant main_interleaved: INTERLEAVE_RESULT, TILE_DIM 16; plus the
+ *     undispatched variants: kernel main = WIDE_SAMPLING / TILE_DIM 32, and SAMPLE_EXHAUSTIVELY),
+ *   Shaders/Upsample.compute:54-233 (variants main / main_blendout; plus main_premin / main_premin_blendout),
  *   AmbientOcclusion.cs:262-281 (formats, sizes), :561-593 (constants), :604-785 (dispatch).
  *
  * Conventions for the fixed-function behaviour the HLSL relies on (D3D11, not in the repo):
@@ -71,12 +72,19 @@ typedef struct MeaoOracle {
     int depth_is_linear;            /* 0: raw depth through Linearize (reference); 1: input already linear */
     MeaoOracleParams params;
     MeaoOracleCamera camera;
+    /* ---- variants the reference ships in its shaders but never dispatches; all 0 = reference behaviour */
+    int sample_exhaustively;        /* Render.compute:144-159 (#define SAMPLE_EXHAUSTIVELY, 68 taps); weight zeroing AO.cs:709-715 skipped */
+    int single_pass_stereo;         /* AO.cs:680: ThicknessMultiplier *= 2 (the width doubling of AO.cs:339 is the caller's) */
+    int high_quality_mask;          /* bit k-1: level k also runs Render.compute kernel "main" (WIDE_SAMPLING, non-tiled source
+                                       LowDepth<k>, AO.cs:679) into HighQuality<k>, and the upsample whose LOW level is k runs
+                                       main_premin / main_premin_blendout with LoResAO2 = HighQuality<k> (Upsample.compute:23,25,58-60) */
     float *linear_depth;            /* id 1      L0      f16   */
     float *low_depth[5];            /* id 2..5   L1..L4  f32   [1..4] */
     float *tiled_depth[5];          /* id 6..9   L3..L6 x16 slices  f16   [1..4] */
     float *occlusion[5];            /* id 10..13 L1..L4  unorm8 [1..4] */
     float *combined[4];             /* id 14..16 L1..L3  unorm8 [1..3] */
     float *result;                  /* id 17     L0      unorm8 */
+    float *high_quality[5];         /* id 18..21 L1..L4  unorm8 [1..4]  (extension ids: not in AO.cs:787-808) */
 } MeaoOracle;
 
 MeaoOracle *meao_oracle_create(int width, int height);
@@ -94,6 +102,10 @@ void meao_oracle_sample_thickness(float out12[12]);
 void meao_oracle_render_constants(const MeaoOracle *o, int level /*1..4*/,
                                   float inv_thickness[12], float sample_weight[12],
                                   float inv_slice_dim[2], float *reject_fadeoff, float *intensity);
+/* same for Render.compute kernel "main" (WIDE_SAMPLING): source = LowDepth<level>, not tiled => AO.cs:679 doubles the thickness */
+void meao_oracle_render_constants_wide(const MeaoOracle *o, int level /*1..4*/,
+                                       float inv_thickness[12], float sample_weight[12],
+                                       float inv_slice_dim[2], float *reject_fadeoff, float *intensity);
 void meao_oracle_upsample_constants(const MeaoOracle *o, int lo_level /*1..4*/,
                                     float inv_low[2], float inv_high[2], float *noise_filter_strength,
                                     float *step_size, float *blur_tolerance, float *upsample_tolerance);
@@ -102,8 +114,17 @@ void meao_oracle_upsample_constants(const MeaoOracle *o, int lo_level /*1..4*/,
  * row-striped; results are identical for any thread count. */
 void meao_oracle_downsample(MeaoOracle *o, const float *depth, int threads);   /* DS1 + DS2 */
 void meao_oracle_render(MeaoOracle *o, int level /*1..4*/, int threads);       /* REN main_interleaved */
-void meao_oracle_upsample(MeaoOracle *o, int lo_level /*4..1*/, int threads);  /* UPS main(_blendout) */
-void meao_oracle_run(MeaoOracle *o, const float *depth, int threads);          /* steps 1..10 */
+void meao_oracle_render_wide(MeaoOracle *o, int level /*1..4*/, int threads);  /* REN main (WIDE_SAMPLING) -> HighQuality<level> */
+void meao_oracle_upsample(MeaoOracle *o, int lo_level /*4..1*/, int threads);  /* UPS main(_blendout); main_premin(_blendout) when bit lo_level-1 of high_quality_mask is set */
+void meao_oracle_run(MeaoOracle *o, const float *depth, int threads);          /* steps 1..10 (+ the high-quality renders selected by high_quality_mask) */
+
+/* Debug views: PushDebugBlitCommands, AO.cs:787-820, followed by Blit.shader pass 3 (:116-134).
+ * Writes the W x H R8 image the _result target holds after the debug blit of buffer <debug_id> (1..17):
+ *   non-tiled source: cmd.Blit(rt, _result) = point-sampled stretch (RTs are FilterMode.Point, AO.cs:206,228,236),
+ *                     texel = floor(uv * size) at the pixel centre uv = ((x+.5)/W, (y+.5)/H), evaluated in exact integers;
+ *   tiled source:     Blit.shader pass 4 (:136-156): uv4 = uv*4, slice = floor(uv4.x) + 4*floor(uv4.y), point sample at frac(uv4);
+ *   id 17: the AO result itself.  The R8 store applies the UNORM8 rule to the sampled value. */
+void meao_oracle_debug_view(const MeaoOracle *o, int debug_id, uint8_t *out_codes);
 
 /* Composite passes.  Fixed-function output-merger blending restated in fp32:
  *   pass 2, Blit.shader:84-101 + "Blend Zero SrcAlpha"                          : dst.rgba *= ao

@@ -29,7 +29,8 @@ class OracleCamera(C.Structure):
 class _OracleStruct(C.Structure):
     _fields_ = [("W", C.c_int), ("H", C.c_int), ("lw", C.c_int * 7), ("lh", C.c_int * 7),
                 ("quantize_storage", C.c_int), ("depth_is_linear", C.c_int),
-                ("params", OracleParams), ("camera", OracleCamera)]
+                ("params", OracleParams), ("camera", OracleCamera),
+                ("sample_exhaustively", C.c_int), ("single_pass_stereo", C.c_int), ("high_quality_mask", C.c_int)]
     # buffer pointers follow; they are reached through meao_oracle_get_buffer
 
 
@@ -65,6 +66,8 @@ def _lib(variant: str = "fma") -> C.CDLL:
         lib.meao_oracle_downsample.argtypes = [C.POINTER(_OracleStruct), fp, C.c_int]
         lib.meao_oracle_render.argtypes = [C.POINTER(_OracleStruct), C.c_int, C.c_int]
         lib.meao_oracle_upsample.argtypes = [C.POINTER(_OracleStruct), C.c_int, C.c_int]
+        lib.meao_oracle_render_wide.argtypes = [C.POINTER(_OracleStruct), C.c_int, C.c_int]
+        lib.meao_oracle_debug_view.argtypes = [C.POINTER(_OracleStruct), C.c_int, C.c_void_p]
         lib.meao_oracle_run.argtypes = [C.POINTER(_OracleStruct), fp, C.c_int]
         lib.meao_oracle_f16_round.restype = C.c_float
         lib.meao_oracle_f16_round.argtypes = [C.c_float]
@@ -77,6 +80,7 @@ def _lib(variant: str = "fma") -> C.CDLL:
         lib.meao_oracle_zbuffer_params.argtypes = [C.POINTER(OracleCamera), fp]
         lib.meao_oracle_sample_thickness.argtypes = [fp]
         lib.meao_oracle_render_constants.argtypes = [C.POINTER(_OracleStruct), C.c_int, fp, fp, fp, fp, fp]
+        lib.meao_oracle_render_constants_wide.argtypes = [C.POINTER(_OracleStruct), C.c_int, fp, fp, fp, fp, fp]
         lib.meao_oracle_upsample_constants.argtypes = [C.POINTER(_OracleStruct), C.c_int, fp, fp, fp, fp, fp, fp]
         lib.meao_oracle_composite_framebuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
         lib.meao_oracle_composite_gbuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
@@ -95,13 +99,16 @@ class Oracle:
     BUFFER_NAMES = {1: "LinearDepth", 2: "LowDepth1", 3: "LowDepth2", 4: "LowDepth3", 5: "LowDepth4",
                     6: "TiledDepth1", 7: "TiledDepth2", 8: "TiledDepth3", 9: "TiledDepth4",
                     10: "Occlusion1", 11: "Occlusion2", 12: "Occlusion3", 13: "Occlusion4",
-                    14: "Combined1", 15: "Combined2", 16: "Combined3", 17: "AmbientOcclusion"}
+                    14: "Combined1", 15: "Combined2", 16: "Combined3", 17: "AmbientOcclusion",
+                    # extension ids (not in AO.cs:787-808): output of Render.compute kernel "main" per level
+                    18: "HighQuality1", 19: "HighQuality2", 20: "HighQuality3", 21: "HighQuality4"}
 
     def __init__(self, width: int, height: int, *, variant: str = "fma", quantize_storage: bool = True,
                  depth_is_linear: bool = False, near: float = 0.3, far: float = 100.0,
                  tan_half_fov_h_: float | None = None, reversed_z: bool = True, threads: int = 1,
                  noise_filter_tolerance: float = 0.0, blur_tolerance: float = -4.6,
-                 upsample_tolerance: float = -12.0, thickness_modifier: float = 1.0, intensity: float = 1.0):
+                 upsample_tolerance: float = -12.0, thickness_modifier: float = 1.0, intensity: float = 1.0,
+                 sample_exhaustively: bool = False, single_pass_stereo: bool = False, high_quality_mask: int = 0):
         self._lib = _lib(variant)
         self._o = self._lib.meao_oracle_create(width, height)
         if not self._o:
@@ -113,6 +120,7 @@ class Oracle:
         s.camera.near_clip, s.camera.far_clip = near, far
         s.camera.tan_half_fov_h = tan_half_fov_h(width, height) if tan_half_fov_h_ is None else tan_half_fov_h_
         s.camera.reversed_z = int(reversed_z)
+        s.sample_exhaustively, s.single_pass_stereo, s.high_quality_mask = int(sample_exhaustively), int(single_pass_stereo), int(high_quality_mask)
         p = s.params
         p.noise_filter_tolerance, p.blur_tolerance, p.upsample_tolerance = noise_filter_tolerance, blur_tolerance, upsample_tolerance
         p.thickness_modifier, p.intensity = thickness_modifier, intensity
@@ -151,8 +159,18 @@ class Oracle:
     def render(self, level: int) -> None:
         self._lib.meao_oracle_render(self._o, level, self.threads)
 
+    def render_wide(self, level: int) -> None:
+        """Render.compute kernel "main" (WIDE_SAMPLING) on LowDepth<level> -> HighQuality<level> (buffer 17 + level)."""
+        self._lib.meao_oracle_render_wide(self._o, level, self.threads)
+
     def upsample(self, lo_level: int) -> None:
         self._lib.meao_oracle_upsample(self._o, lo_level, self.threads)
+
+    def debug_view(self, debug_id: int) -> np.ndarray:
+        """The W x H R8 image PushDebugBlitCommands (AO.cs:787-820) leaves in _result for buffer <debug_id>."""
+        out = np.zeros((self.height, self.width), np.uint8)
+        self._lib.meao_oracle_debug_view(self._o, debug_id, out.ctypes.data)
+        return out
 
     def run(self, depth: np.ndarray) -> np.ndarray:
         d = self._depth(depth)
@@ -174,8 +192,8 @@ class Oracle:
         self.buffer(debug_id)[...] = np.asarray(values, dtype=np.float32)
 
     def codes(self, debug_id: int) -> np.ndarray:
-        """UNORM8 buffer (ids 10..17) as uint8 codes."""
-        assert 10 <= debug_id <= 17
+        """UNORM8 buffer (ids 10..21) as uint8 codes."""
+        assert 10 <= debug_id <= 21
         return np.rint(self.buffer(debug_id) * 255.0).astype(np.uint8)
 
     def ao_u8(self) -> np.ndarray:
@@ -192,10 +210,11 @@ class Oracle:
         self._lib.meao_oracle_sample_thickness(self._fptr(out))
         return out
 
-    def render_constants(self, level: int) -> dict:
+    def render_constants(self, level: int, wide: bool = False) -> dict:
         it, sw, isd = np.zeros(12, np.float32), np.zeros(12, np.float32), np.zeros(2, np.float32)
         rf, inten = C.c_float(), C.c_float()
-        self._lib.meao_oracle_render_constants(self._o, level, self._fptr(it), self._fptr(sw), self._fptr(isd),
+        fn = self._lib.meao_oracle_render_constants_wide if wide else self._lib.meao_oracle_render_constants
+        fn(self._o, level, self._fptr(it), self._fptr(sw), self._fptr(isd),
                                                C.byref(rf), C.byref(inten))
         return {"inv_thickness": it, "sample_weight": sw, "inv_slice_dim": isd,
                 "reject_fadeoff": np.float32(rf.value), "intensity": np.float32(inten.value)}

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (meao_[a-z0-9_]+)", out))
     assert set(decl) <= exported
-    assert lib.meao_abi_version() == 1
+    assert lib.meao_abi_version() == 2
 
 
 def test_library_has_no_driver_link_dependency():
@@ -151,3 +151,52 @@ def test_pure_c_client_plans_without_gpu(tmp_path):
     exe = _build_c_client(tmp_path)
     r = subprocess.run([exe, "plan"], capture_output=True, text=True)
     assert r.returncode == 0 and "plan ok" in r.stdout, r.stderr
+
+
+# ---- variants: planner side, no GPU ------------------------------------------------------
+@pytest.mark.parametrize("W,H", [(3840, 2160), (641, 363)])
+@pytest.mark.parametrize("exh,stereo", [(False, False), (True, False), (False, True), (True, True)])
+def test_variant_constants_equal_oracle_constants(W, H, exh, stereo):
+    cam = Camera(W // 2 if stereo else W, H, stereoEnabled=stereo)
+    ao = AmbientOcclusion(cam, device=-1)
+    ao.sampleExhaustively = exh
+    ao.highQualityMask = 0b1010
+    if stereo:
+        ao.OnPreRender()                                         # one draw for both eyes => singlePassStereoEnabled (AO.cs:392-401)
+    assert ao.LateUpdate() is True
+    assert (ao._width, ao._height) == (2 * cam.pixelWidth if stereo else cam.pixelWidth, H)      # AO.cs:338-341
+    # tanHalfFovH comes from the camera's own projection matrix (AO.cs:570-573), i.e. the single-eye aspect
+    o = Oracle(ao._width, H, tan_half_fov_h_=1.0 / cam.projection00, sample_exhaustively=exh, single_pass_stereo=stereo, high_quality_mask=0b1010)
+    for k in range(1, 5):
+        for wide in (False, True):
+            a, b = ao.render_constants(k, wide=wide), o.render_constants(k, wide=wide)
+            for key in a:
+                assert np.array_equal(np.asarray(a[key]), np.asarray(b[key])), (k, wide, key)
+    assert ao.kernels_per_frame == 11
+    v = N.MeaoVariants()
+    N.check(ao._ctx, N.lib().meao_get_variants(ao._ctx, C.byref(v)))
+    assert (v.single_pass_stereo, v.sample_exhaustively, v.high_quality_mask) == (int(stereo), int(exh), 0b1010)
+
+
+def test_variant_change_detection_and_stereo_hack():
+    """A variant change re-plans like a property change; the stereo detection keeps the reference's one-frame lag
+    semantics (AO.cs:387-401: stereo is recognised only in a frame that saw exactly ONE OnPreRender)."""
+    cam = Camera(640, 360, stereoEnabled=True)
+    ao = AmbientOcclusion(cam, device=-1)
+    assert ao.LateUpdate() is True and ao._width == 640        # no draw seen yet: not stereo (the first-frame glitch)
+    ao.OnPreRender()
+    assert ao.LateUpdate() is True and ao._width == 1280       # one draw for both eyes
+    ao.OnPreRender(); ao.OnPreRender()
+    assert ao.LateUpdate() is True and ao._width == 640        # multi-pass stereo: two draws
+    ao.OnPreRender()
+    cam.targetTexture = object()
+    assert ao.LateUpdate() is False and ao._width == 640       # rendering to a texture: never single-pass (AO.cs:398)
+    cam.targetTexture = None
+    ao.sampleExhaustively = True
+    assert ao.LateUpdate() is True
+    assert ao.LateUpdate() is False
+    ao.highQualityMask = 15
+    assert ao.LateUpdate() is True and ao.kernels_per_frame == 13
+    ao.highQualityMask = 16
+    with pytest.raises(MeaoError):
+        ao.LateUpdate()

@@ -235,3 +235,97 @@ def test_composite_oracle_identities():
     assert np.array_equal(g3[..., 3], c16[..., 3]) and not g3[..., :3].any()
     g0, g3 = O.composite_gbuffer(one, c8, c8)
     assert np.array_equal(g0, c8) and np.array_equal(g3, c8)
+
+
+# ---- variants the reference ships but never dispatches ---------------------------------
+def _run_both(W, H, seed, **kw):
+    o = Oracle(W, H, variant="nofma", **kw)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=seed))
+    ao = o.run(depth)
+    rc = {k: o.render_constants(k) for k in range(1, 5)}
+    rcw = {k: o.render_constants(k, wide=True) for k in range(1, 5)}
+    uc = {k: o.upsample_constants(k) for k in range(1, 5)}
+    r = DF.run(depth, rc, uc, o.zbuffer_params(), return_all=True, exhaustive=kw.get("sample_exhaustively", False),
+               high_quality_mask=kw.get("high_quality_mask", 0), render_consts_wide=rcw)
+    return o, ao, r
+
+
+@pytest.mark.parametrize("W,H,kw", [
+    (250, 131, dict(sample_exhaustively=True)),
+    (97, 203, dict(high_quality_mask=0b1111)),
+    (130, 70, dict(high_quality_mask=0b0101, sample_exhaustively=True, intensity=1.2)),
+    (64, 48, dict(high_quality_mask=0b1000, single_pass_stereo=True)),
+    (33, 17, dict(high_quality_mask=0b0011, thickness_modifier=3.0)),
+    (5, 3, dict(high_quality_mask=0b1111, sample_exhaustively=True)),
+])
+def test_variants_direct_formulation_equals_thread_group_oracle(W, H, kw):
+    """Render.compute kernel `main` (WIDE_SAMPLING, 32x32 LDS tile, 16x16 threads), SAMPLE_EXHAUSTIVELY and the
+    Upsample.compute main_premin* kernels: global per-pixel restatement == literal thread-group restatement."""
+    o, ao, r = _run_both(W, H, W * 3 + H, **kw)
+    for k in range(1, 5):
+        assert np.array_equal(r["occ"][k], o.codes(9 + k)), f"Occlusion{k}"
+        if (kw.get("high_quality_mask", 0) >> (k - 1)) & 1:
+            assert np.array_equal(r["hq"][k], o.codes(17 + k)), f"HighQuality{k}"
+    for k in range(1, 4):
+        assert np.array_equal(r["comb"][k], o.codes(13 + k)), f"Combined{k}"
+    assert np.array_equal(r["comb"][0], ao)
+
+
+def test_exhaustive_weights_and_stereo_thickness():
+    """AO.cs:696-724 without the zeroing of :709-715: all twelve weights, still normalised; AO.cs:679-680 double the
+    thickness (halve InvThicknessTable) for a non-tiled source and again for single-pass stereo."""
+    W, H = 3840, 2160
+    base, exh = Oracle(W, H), Oracle(W, H, sample_exhaustively=True)
+    w = exh.render_constants(1)["sample_weight"]
+    t = exh.sample_thickness()
+    mult = np.array([4, 4, 4, 4, 4, 8, 8, 8, 4, 8, 8, 4], np.float32)
+    assert np.all(w > 0) and abs(float(w.astype(np.float64).sum()) - 1.0) < 3e-7
+    assert np.allclose(w, mult * t / np.float32((mult * t).astype(np.float64).sum()), rtol=1e-6)
+    assert np.array_equal(exh.render_constants(1)["inv_thickness"], base.render_constants(1)["inv_thickness"])
+    st = Oracle(W, H, single_pass_stereo=True)
+    assert np.array_equal(st.render_constants(2)["inv_thickness"] * np.float32(2), base.render_constants(2)["inv_thickness"])
+    # wide: source = LowDepth<k> (width lw[k] = 4 * lw[k+2]) and x2 for !isTiled => TM is half the tiled one
+    a, b = base.render_constants(3, wide=True), base.render_constants(3)
+    assert np.allclose(a["inv_thickness"], b["inv_thickness"] * np.float32(2), rtol=1e-6)
+    assert a["inv_slice_dim"][0] == np.float32(1.0 / 480) and b["inv_slice_dim"][0] == np.float32(1.0 / 120)
+
+
+@pytest.mark.parametrize("W,H", [(256, 256), (192, 128)])
+def test_variants_constant_depth_is_all_255(W, H):
+    """P5(i) carries over: constant depth => every pair = 1 in either sample set and either kernel; min(255, 255) = 255."""
+    o = Oracle(W, H, sample_exhaustively=True, high_quality_mask=15)
+    ao = o.run(synth.lin01_to_raw(np.full((H, W), 0.1, np.float32)))
+    assert int((ao != 255).sum()) == 0
+    for bid in list(range(10, 17)) + [18, 19, 20, 21]:
+        assert int((o.codes(bid) != 255).sum()) == 0, bid
+
+
+def test_premin_never_brightens():
+    """LoResAO1 = min(LoResAO1, LoResAO2) feeds a blur + upsample that are monotone in the low-res AO
+    (non-negative weights), so enabling the high-quality pass can only darken the combined buffers."""
+    W, H = 200, 120
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, 12))
+    a, b = Oracle(W, H), Oracle(W, H, high_quality_mask=15)
+    a.run(depth), b.run(depth)
+    for bid in (14, 15, 16, 17):
+        assert np.all(b.codes(bid).astype(int) <= a.codes(bid).astype(int) + 1), bid     # +1: unorm8 rounding of a ratio of sums
+    assert (b.codes(17).astype(int) < a.codes(17).astype(int)).mean() > 0.05
+
+
+@pytest.mark.parametrize("W,H", [(256, 256), (130, 70), (83, 61)])
+def test_debug_views_two_restatements(W, H):
+    """PushDebugBlitCommands (AO.cs:787-820) + Blit.shader pass 4: C loop == vectorised numpy; structural checks."""
+    o = Oracle(W, H, intensity=1.1)
+    o.run(synth.lin01_to_raw(synth.random_depth(W, H, 2)))
+    for bid in range(1, 18):
+        assert np.array_equal(o.debug_view(bid), DF.debug_view(o.buffer(bid), W, H)), bid
+    assert np.array_equal(o.debug_view(17), o.codes(17))                         # _debug == 17 shows _result itself
+    v = o.debug_view(10)                                                          # half-res R8 source: every texel shown 2 x 2
+    if W % 2 == 0 and H % 2 == 0:
+        assert np.array_equal(v[::2, ::2], o.codes(10)) and np.array_equal(v[1::2, 1::2], o.codes(10))
+    if (W, H) == (256, 256):                                                      # de-tile: 4 x 4 mosaic of 64 x 64 cells showing 32 x 32 slices 2 x 2
+        t = o.buffer(6)
+        m = o.debug_view(6)
+        for s in (0, 7, 15):
+            cell = m[64 * (s >> 2): 64 * (s >> 2) + 64, 64 * (s & 3): 64 * (s & 3) + 64]
+            assert np.array_equal(cell[::2, ::2], DF._unorm8(t[s]))
