@@ -41,10 +41,15 @@ namespace MiniEngineAO
         [StructLayout(LayoutKind.Sequential)]
         public struct MeaoDeviceCfg { public int device; public uint flags; }
 
+        // Variants the reference ships in its shaders but never selects (meao.h: MeaoVariants); all zero = reference behaviour.
+        [StructLayout(LayoutKind.Sequential)]
+        public struct MeaoVariants { public int single_pass_stereo, sample_exhaustively, high_quality_mask; }
+
         [DllImport(Lib)] public static extern int meao_create(ref MeaoDeviceCfg cfg, out IntPtr ctx);
         [DllImport(Lib)] public static extern void meao_destroy(IntPtr ctx);
         [DllImport(Lib)] public static extern IntPtr meao_last_error(IntPtr ctx);
         [DllImport(Lib)] public static extern int meao_set_params(IntPtr ctx, ref MeaoParams p);
+        [DllImport(Lib)] public static extern int meao_set_variants(IntPtr ctx, ref MeaoVariants v);
         [DllImport(Lib)] public static extern int meao_set_camera(IntPtr ctx, ref MeaoCamera c);
         [DllImport(Lib)] public static extern int meao_resize(IntPtr ctx, int width, int height);
         [DllImport(Lib)] public static extern int meao_render(IntPtr ctx, IntPtr depthDev, int depthKind, IntPtr aoOutDev, IntPtr stream);
@@ -54,6 +59,7 @@ namespace MiniEngineAO
         [DllImport(Lib)] public static extern int meao_composite_framebuffer(IntPtr ctx, IntPtr aoDev, IntPtr colorDev, int colorFormat, IntPtr stream);
         [DllImport(Lib)] public static extern int meao_composite_gbuffer(IntPtr ctx, IntPtr aoDev, IntPtr gbuffer0Dev, IntPtr gbuffer3Dev, int gbuffer3Format, IntPtr stream);
         [DllImport(Lib)] public static extern int meao_get_buffer(IntPtr ctx, int bufferId, IntPtr hostOut, UIntPtr hostBytes);
+        [DllImport(Lib)] public static extern int meao_debug_view(IntPtr ctx, int bufferId, IntPtr outR8Dev, IntPtr stream);   // AO.cs:787-820
 
         public static void Check(IntPtr ctx, int rc)
         {
@@ -85,6 +91,16 @@ namespace MiniEngineAO
 
         [SerializeField] bool _ambientOnly = true;
         public bool ambientOnly { get { return _ambientOnly; } set { _ambientOnly = value; } }
+
+        // ---- not in the reference inspector: the shader variants Render.compute / Upsample.compute ship but AO.cs never selects ----
+        [SerializeField] bool _sampleExhaustively;             // Render.compute:144-159, AmbientOcclusion.cs:709-715 (FIXME there)
+        [SerializeField, Range(0, 15)] int _highQualityMask;   // bit k-1: Render kernel "main" on level k + Upsample "main_premin*"
+        int _drawCountPerFrame;                                // AmbientOcclusion.cs:289, 349-355: single-pass stereo detection
+        void OnPreRender() { _drawCountPerFrame++; }
+        bool singlePassStereoEnabled                           // AmbientOcclusion.cs:392-401
+        {
+            get { return _camera != null && _camera.stereoEnabled && _camera.targetTexture == null && _drawCountPerFrame == 1; }
+        }
 
         const int kEventId = 0x4d41;   // "MA"
 
@@ -123,8 +139,16 @@ namespace MiniEngineAO
                 reversed_z = SystemInfo.usesReversedZBuffer ? 1 : 0                          // :564
             };
             MeaoNative.Check(_ctx, MeaoNative.meao_set_camera(_ctx, ref cam));
-            rebuild |= MeaoNative.meao_resize(_ctx, _camera.pixelWidth, _camera.pixelHeight) == 1;
+            var stereo = singlePassStereoEnabled;
+            var variants = new MeaoNative.MeaoVariants
+            {
+                single_pass_stereo = stereo ? 1 : 0,                                         // :680
+                sample_exhaustively = _sampleExhaustively ? 1 : 0, high_quality_mask = _highQualityMask
+            };
+            rebuild |= MeaoNative.meao_set_variants(_ctx, ref variants) == 1;
+            rebuild |= MeaoNative.meao_resize(_ctx, _camera.pixelWidth * (stereo ? 2 : 1), _camera.pixelHeight) == 1;   // :338-341
             rebuild |= !Application.isPlaying;                                               // :345
+            _drawCountPerFrame = 0;                                                          // :349
 
             if (rebuild || _renderCommand == null) RebuildCommandBuffers();
         }

@@ -27,6 +27,8 @@ class Camera:
     usesReversedZBuffer: bool = True    # SystemInfo.usesReversedZBuffer on D3D11/12
     stereoEnabled: bool = False         # Camera.stereoEnabled (AO.cs:397)
     targetTexture: object = None        # Camera.targetTexture (AO.cs:398)
+    allowHDR: bool = True               # Camera.allowHDR (AO.cs:407)
+    actualRenderingPath: str = "Forward"    # "Forward" | "DeferredShading" (AO.cs:408)
 
     @property
     def aspect(self) -> float:
@@ -214,6 +216,35 @@ class AmbientOcclusion:
             self._check(self._lib.meao_render_host_async(self._ctx, d.ctypes.data, kind, o.ctypes.data, slot))
         self._check(self._lib.meao_host_wait(self._ctx, 0))
         self._check(self._lib.meao_host_wait(self._ctx, 1))
+
+    # ---- event / pass selection (AO.cs:403-429, 822-839) ---------------------------------------------------
+    @property
+    def ambientOnlyEnabled(self) -> bool:
+        cam = self._camera
+        return bool(self._ambientOnly and cam.allowHDR and cam.actualRenderingPath == "DeferredShading")     # AO.cs:403-410
+
+    @property
+    def camera_events(self) -> tuple[str, str]:
+        """(event of the render command buffer, event of the composite command buffer), RegisterCommandBuffers AO.cs:412-429."""
+        render = "BeforeReflections" if self.ambientOnlyEnabled else "BeforeImageEffects"
+        if self._debug > 0:
+            comp = "AfterImageEffects"
+        else:
+            comp = "BeforeLighting" if self.ambientOnlyEnabled else "BeforeImageEffects"
+        return render, comp
+
+    def composite(self, ao, *, color=None, gbuffer0=None, gbuffer3=None, stream=None) -> str:
+        """PushCompositeCommands (AO.cs:822-839): the ambient-only deferred branch multiplies the G-buffer occlusion and
+        ambient targets (Blit.shader pass 1), otherwise the frame buffer (pass 2).  Returns the branch taken."""
+        if self.ambientOnlyEnabled:
+            if gbuffer0 is None or gbuffer3 is None:
+                raise ValueError("ambient-only deferred composite needs gbuffer0 and gbuffer3 (AO.cs:595-598)")
+            self.composite_gbuffer(ao, gbuffer0, gbuffer3, stream=stream)
+            return "gbuffer"
+        if color is None:
+            raise ValueError("frame-buffer composite needs the camera target")
+        self.composite_framebuffer(ao, color, stream=stream)
+        return "framebuffer"
 
     # ---- composite (Blit.shader passes 1 / 2, AO.cs:822-839) -------------------------------------------
     def composite_framebuffer(self, ao, color, *, stream=None) -> None:

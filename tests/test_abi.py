@@ -200,3 +200,21 @@ def test_variant_change_detection_and_stereo_hack():
     ao.highQualityMask = 16
     with pytest.raises(MeaoError):
         ao.LateUpdate()
+
+
+def test_event_and_composite_pass_selection():
+    """RegisterCommandBuffers / ambientOnlyEnabled (AO.cs:403-429): which camera events and which composite pass."""
+    ao = AmbientOcclusion(Camera(64, 64), device=-1)
+    assert ao.ambientOnlyEnabled is False and ao.camera_events == ("BeforeImageEffects", "BeforeImageEffects")
+    ao.camera.actualRenderingPath = "DeferredShading"
+    assert ao.ambientOnlyEnabled is True and ao.camera_events == ("BeforeReflections", "BeforeLighting")
+    ao.camera.allowHDR = False
+    assert ao.ambientOnlyEnabled is False
+    ao.camera.allowHDR = True
+    ao.ambientOnly = False
+    assert ao.ambientOnlyEnabled is False
+    ao.ambientOnly = True
+    ao._debug = 6
+    assert ao.camera_events == ("BeforeReflections", "AfterImageEffects")
+    with pytest.raises(ValueError):
+        ao.composite(None, color=None)

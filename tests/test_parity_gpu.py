@@ -22,13 +22,22 @@ def torch_cuda():
 
 
 def _mk(W, H, **params):
+    """CUDA host + oracle with the same parameters.  Variant keys: sample_exhaustively,
+    high_quality_mask, single_pass_stereo (W is then the DOUBLE-WIDE eye pair; the camera is W/2 wide)."""
     from miniengineao_b200 import AmbientOcclusion, Camera
     from oracle.oracle import Oracle
     cam_kw = {}
     if "reversed_z" in params:
         cam_kw["usesReversedZBuffer"] = params["reversed_z"]
-    ao = AmbientOcclusion(Camera(W, H, **cam_kw), device=0, use_graph=params.pop("use_graph", True))
-    okw = {}
+    stereo = bool(params.get("single_pass_stereo", False))
+    cam = Camera(W // 2 if stereo else W, H, stereoEnabled=stereo, **cam_kw)
+    ao = AmbientOcclusion(cam, device=0, use_graph=params.pop("use_graph", True))
+    ao.sampleExhaustively = bool(params.get("sample_exhaustively", False))
+    ao.highQualityMask = int(params.get("high_quality_mask", 0))
+    okw = {k: params[k] for k in ("sample_exhaustively", "high_quality_mask", "single_pass_stereo") if k in params}
+    if stereo:
+        ao.OnPreRender()                    # one draw for both eyes (AO.cs:352-355, 392-401)
+        okw["tan_half_fov_h_"] = 1.0 / cam.projection00
     for py, cs in (("noise_filter_tolerance", "noiseFilterTolerance"), ("blur_tolerance", "blurTolerance"),
                    ("upsample_tolerance", "upsampleTolerance"), ("thickness_modifier", "thicknessModifier"),
                    ("intensity", "intensity")):
@@ -41,10 +50,10 @@ def _mk(W, H, **params):
     return ao, orc
 
 
-def _compare_all(ao, orc, tag):
-    """Every debug buffer 1..17 of the CUDA path against the oracle, bit for bit."""
+def _compare_all(ao, orc, tag, extra=()):
+    """Every debug buffer 1..17 (+ extension ids in `extra`) of the CUDA path against the oracle, bit for bit."""
     bad = []
-    for bid in range(1, 18):
+    for bid in list(range(1, 18)) + list(extra):
         got = ao.debug_buffer(bid)
         ref = orc.buffer(bid)
         if got.dtype == np.uint8:
@@ -491,3 +500,211 @@ def test_random_configurations_bit_exact(torch_cuda):
         assert np.array_equal(got, ref), (i, W, H, params)
         _compare_all(ao, orc, f"cfg {i}: {W}x{H} {params}")
         ao.close()
+
+
+# ---- variants the reference ships but never dispatches ---------------------------------------
+def _hq_ids(mask):
+    return [17 + k for k in range(1, 5) if (mask >> (k - 1)) & 1]
+
+
+VARIANTS = [
+    dict(sample_exhaustively=True),
+    dict(high_quality_mask=0b1111),
+    dict(high_quality_mask=0b1000, intensity=1.1),
+    dict(high_quality_mask=0b0110, sample_exhaustively=True, thickness_modifier=2.5, intensity=1.3),
+    dict(single_pass_stereo=True),
+    dict(single_pass_stereo=True, high_quality_mask=0b1111, sample_exhaustively=True, reversed_z=False),
+]
+
+
+@pytest.mark.parametrize("W,H", [(256, 256), (130, 70), (322, 190), (640, 360), (1000, 38), (38, 1000), (6, 4)])
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_variants_full_pipe_bit_exact(torch_cuda, W, H, variant):
+    """Render.compute kernel `main` (WIDE_SAMPLING) -> HighQuality<k>, SAMPLE_EXHAUSTIVELY, Upsample.compute main_premin*
+    and the single-pass-stereo thickness: whole pipe + every intermediate against the oracle, bit for bit."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    ao, orc = _mk(W, H, **variant)
+    rz = variant.get("reversed_z", True)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=W * 5 + H), reversed_z=rz)
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    mask = variant.get("high_quality_mask", 0)
+    assert ao.kernels_per_frame == 9 + bin(mask).count("1") and ao.launch_count == ao.kernels_per_frame
+    assert int((got != ref).sum()) == 0, variant
+    _compare_all(ao, orc, f"{W}x{H} {variant}", extra=_hq_ids(mask))
+
+
+def test_variants_1080p_corridor_and_sky(torch_cuda):
+    """BASELINE.json configs[1] geometry with every variant on, plus sky pixels (inf / NaN semantics in the f32 wide path)."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 1920, 1080
+    ao, orc = _mk(W, H, intensity=1.1, high_quality_mask=15, sample_exhaustively=True)
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    depth[100:180, 300:700] = 0.0
+    depth[::37, ::29] = 0.0
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert int((got != ref).sum()) == 0
+    _compare_all(ao, orc, "1080p variants", extra=[18, 19, 20, 21])
+
+
+def test_variants_4k_matches_oracle(torch_cuda):
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 3840, 2160
+    ao, orc = _mk(W, H, intensity=1.1, high_quality_mask=0b1100)
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert int((got != ref).sum()) == 0
+    for bid in (20, 21):
+        assert np.array_equal(ao.debug_buffer(bid), orc.codes(bid)), bid
+
+
+def test_stage_render_wide_and_premin_with_injected_inputs(torch_cuda):
+    """The two new stage entry points alone, fed the ORACLE's inputs: meao_stage_render_wide per level, and
+    meao_stage_upsample running the premin kernels (main_premin_blendout for 4->3..2->1, main_premin for 1->0)."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 330, 170
+    ao, orc = _mk(W, H, intensity=1.2, high_quality_mask=15)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=31))
+    orc.run(depth)
+    ao.stage_downsample(torch.from_numpy(depth).cuda())
+    for k in range(1, 5):
+        ao.set_debug_buffer(1 + k, orc.buffer(1 + k))
+        ao.stage_render_wide(k)
+        assert np.array_equal(ao.debug_buffer(17 + k), orc.codes(17 + k)), f"render_wide level {k}"
+    for lo in range(4, 0, -1):
+        hi = lo - 1
+        ao.set_debug_buffer(1 + lo, orc.buffer(1 + lo))
+        ao.set_debug_buffer(13 if lo == 4 else 13 + lo, orc.codes(13 if lo == 4 else 13 + lo))
+        ao.set_debug_buffer(17 + lo, orc.codes(17 + lo))
+        if hi > 0:
+            ao.set_debug_buffer(1 + hi, orc.buffer(1 + hi))
+            ao.set_debug_buffer(9 + hi, orc.codes(9 + hi))
+        else:
+            ao.set_debug_buffer(1, orc.buffer(1).astype(np.float16))
+        ao.stage_upsample(lo)
+        out_id = 17 if hi == 0 else 13 + hi
+        assert np.array_equal(ao.debug_buffer(out_id), orc.codes(out_id)), f"premin upsample {lo}->{hi}"
+
+
+def test_variant_switch_replans_and_graph_counts(torch_cuda):
+    """Toggling a variant between frames re-plans (drops the captured graph) and the next frame matches the oracle."""
+    from miniengineao_b200 import synth
+    from oracle.oracle import Oracle
+    torch = torch_cuda
+    W, H = 320, 200
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, 77))
+    d = torch.from_numpy(depth).cuda()
+    ao, _ = _mk(W, H)
+    seq = [dict(), dict(high_quality_mask=5), dict(high_quality_mask=5, sample_exhaustively=True), dict(sample_exhaustively=True), dict()]
+    launches = 0
+    for v in seq:
+        ao.highQualityMask = v.get("high_quality_mask", 0)
+        ao.sampleExhaustively = v.get("sample_exhaustively", False)
+        for _ in range(2):          # second call replays the graph
+            got = ao.render(d).cpu().numpy()
+            launches += 9 + bin(ao.highQualityMask).count("1")
+        assert np.array_equal(got, Oracle(W, H, threads=8, **v).run(depth)), v
+    assert ao.launch_count == launches
+
+
+@pytest.mark.parametrize("W,H,bands", [(1920, 1080, 2), (2560, 1440, 3)])
+def test_row_bands_with_variants_equal_whole_frame(torch_cuda, W, H, bands):
+    """Tile-vs-whole equality with the high-quality passes on: HighQuality<k> needs only +-8 rows of LowDepth<k>,
+    inside the halo the interleaved render already exchanges."""
+    from miniengineao_b200 import AmbientOcclusion, Camera, rowtile, synth
+    torch = torch_cuda
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+
+    def mk():
+        a = AmbientOcclusion(Camera(W, H), device=0)
+        a.highQualityMask, a.sampleExhaustively = 15, True
+        return a
+    ref = mk().render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    cuts = rowtile.partition(H, bands)
+    ctxs, send, recv = [], [], []
+    for i in range(bands):
+        a = mk()
+        a.set_row_band(cuts[i], cuts[i + 1], *rowtile.neighbours(cuts, i))
+        ctxs.append(a)
+        mkb = lambda n: torch.empty(int(n), dtype=torch.uint8, device="cuda")  # noqa: E731
+        send.append([mkb(a.halo_bytes(0)), mkb(a.halo_bytes(1))])
+        recv.append([mkb(a.halo_recv_bytes(0)), mkb(a.halo_recv_bytes(1))])
+    dts = [torch.from_numpy(depth[cuts[i]:cuts[i + 1]]).cuda() for i in range(bands)]
+    outs = [torch.zeros((cuts[i + 1] - cuts[i], W), dtype=torch.uint8, device="cuda") for i in range(bands)]
+    for i, a in enumerate(ctxs):
+        a.band_phase_a(dts[i], send[i][0], send[i][1])
+    torch.cuda.synchronize()
+    for i in range(bands - 1):
+        recv[i + 1][0].copy_(send[i][1])
+        recv[i][1].copy_(send[i + 1][0])
+    torch.cuda.synchronize()
+    for i, a in enumerate(ctxs):
+        a.band_phase_b(recv[i][0], recv[i][1], outs[i])
+    torch.cuda.synchronize()
+    got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+    assert int((got != ref).sum()) == 0
+
+
+@pytest.mark.parametrize("W,H", [(256, 256), (130, 70), (321, 203), (1920, 1080)])
+def test_debug_views_bit_exact(torch_cuda, W, H):
+    """PushDebugBlitCommands (AO.cs:787-820) for every value of the `debug` property (1..17) plus the
+    HighQuality extension ids, incl. the Detile pass (Blit.shader:136-156) over the VIRTUAL atlases."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    ao, orc = _mk(W, H, intensity=1.1, high_quality_mask=0b0101)
+    depth = synth.lin01_to_raw(synth.corridor(W, H) if W >= 1000 else synth.random_depth(W, H, seed=4))
+    ref = orc.run(depth)
+    out = ao.render(torch.from_numpy(depth).cuda())
+    for bid in list(range(1, 18)) + [18, 20]:
+        got = ao.debug_view(bid)
+        ao.synchronize()
+        assert np.array_equal(got.cpu().numpy(), orc.debug_view(bid)), (bid, ao.DEBUG_NAMES[bid])
+    assert np.array_equal(out.cpu().numpy(), ref)                      # the frame's own output is untouched by the views
+
+
+def test_debug_view_dump_is_a_valid_pgm(torch_cuda, tmp_path):
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 160, 90
+    ao, orc = _mk(W, H)
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    orc.run(depth)
+    ao.render(torch.from_numpy(depth).cuda())
+    path = str(tmp_path / "tiled1.pgm")
+    ao.dump_debug_view(6, path)
+    raw = open(path, "rb").read()
+    header = b"P5\n%d %d\n255\n" % (W, H)
+    assert raw.startswith(header) and len(raw) == len(header) + W * H
+    assert np.array_equal(np.frombuffer(raw[len(header):], np.uint8).reshape(H, W), orc.debug_view(6))
+
+
+def test_composite_branch_selection(torch_cuda):
+    """PushCompositeCommands (AO.cs:822-839): forward / non-HDR cameras multiply the frame buffer (pass 2), the
+    ambient-only deferred HDR case multiplies GBuffer0.a and the ambient target (pass 1)."""
+    from miniengineao_b200 import synth
+    from oracle import oracle as O
+    torch = torch_cuda
+    W, H = 320, 180
+    ao, orc = _mk(W, H)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=8))
+    ref_ao = orc.run(depth)
+    ao_dev = ao.render(torch.from_numpy(depth).cuda())
+    rng = np.random.default_rng(5)
+    c16 = rng.uniform(0, 3, size=(H, W, 4)).astype(np.float16)
+    g0 = rng.integers(0, 256, size=(H, W, 4), dtype=np.uint8)
+    col = torch.from_numpy(c16.copy()).cuda()
+    assert ao.composite(ao_dev, color=col) == "framebuffer"
+    torch.cuda.synchronize()
+    assert np.array_equal(col.cpu().numpy().view(np.uint16), O.composite_framebuffer(ref_ao, c16).view(np.uint16))
+    ao.camera.actualRenderingPath = "DeferredShading"
+    g0d, g3d = torch.from_numpy(g0.copy()).cuda(), torch.from_numpy(c16.copy()).cuda()
+    assert ao.composite(ao_dev, gbuffer0=g0d, gbuffer3=g3d) == "gbuffer"
+    torch.cuda.synchronize()
+    e0, e3 = O.composite_gbuffer(ref_ao, g0, c16)
+    assert np.array_equal(g0d.cpu().numpy(), e0) and np.array_equal(g3d.cpu().numpy().view(np.uint16), e3.view(np.uint16))
