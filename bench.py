@@ -429,7 +429,7 @@ def main() -> None:
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rowtile", action="store_true", help="skip the row-tiled 8K measurement (N > 1 only)")
-    ap.add_argument("--streams", type=int, default=3, help="contexts/streams that frames alternate over (1 = serial frames)")
+    ap.add_argument("--streams", type=int, default=5, help="contexts/streams that frames alternate over (1 = serial frames)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -21,19 +21,21 @@ __global__ void __launch_bounds__(256) debug_view_kernel(const DebugViewArgs a)
 #ifdef MEAO_DEVICE_OK
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= a.W) return;
+    // 32-bit unsigned arithmetic is exact here: W, H <= 32768 (meao_resize), so (2x+1) * sw < 2^31 and r * sw < 2^29
+    const uint32_t W2 = 2u * (uint32_t)a.W, H2 = 2u * (uint32_t)a.H;
     float v;
     if (a.tiled) {
         // Blit.shader:150-152: uv4 = uv * 4; slice = floor(uv4.x) + floor(uv4.y) * 4; sample the slice at frac(uv4)
-        const long long nx = 8LL * x + 4, ny = 8LL * y + 4;                 // 4 * uv = n / (2 * size)
-        const int qx = (int)(nx / (2LL * a.W)), qy = (int)(ny / (2LL * a.H));
-        const long long rx = nx - 2LL * a.W * qx, ry = ny - 2LL * a.H * qy; // frac = r / (2 * size)
-        const int tx = (int)(rx * a.sw / (2LL * a.W)), ty = (int)(ry * a.sh / (2LL * a.H));
-        const int px = 4 * tx + qx, py = 4 * ty + qy;                       // inverse of DS1:69,71 with slice = qx | qy << 2
+        const uint32_t nx = 8u * x + 4u, ny = 8u * y + 4u;                  // 4 * uv = n / (2 * size)
+        const uint32_t qx = nx / W2, qy = ny / H2;
+        const uint32_t rx = nx - W2 * qx, ry = ny - H2 * qy;                // frac = r / (2 * size)
+        const int tx = (int)(rx * (uint32_t)a.sw / W2), ty = (int)(ry * (uint32_t)a.sh / H2);
+        const int px = 4 * tx + (int)qx, py = 4 * ty + (int)qy;             // inverse of DS1:69,71 with slice = qx | qy << 2
         v = a.pad;
         if (px < a.lw && py < a.lh) v = f16_round(reinterpret_cast<const float *>(a.src)[(size_t)py * a.spitch + px]);
     } else {
         // cmd.Blit(rt, _result), AO.cs:817
-        const int tx = (int)((2LL * x + 1) * a.sw / (2LL * a.W)), ty = (int)((2LL * y + 1) * a.sh / (2LL * a.H));
+        const int tx = (int)((2u * x + 1u) * (uint32_t)a.sw / W2), ty = (int)((2u * y + 1u) * (uint32_t)a.sh / H2);
         const size_t i = (size_t)ty * a.spitch + tx;
         if (a.elem == 1) { a.out[(size_t)y * a.out_pitch + x] = reinterpret_cast<const uint8_t *>(a.src)[i]; return; }   // R8 -> R8: store(load(k)) == k
         v = (a.elem == 2) ? __half2float(reinterpret_cast<const __half *>(a.src)[i]) : reinterpret_cast<const float *>(a.src)[i];
