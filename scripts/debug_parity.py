@@ -8,8 +8,10 @@ from oracle.oracle import Oracle
 W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (256, 256)
 graph = os.environ.get("GRAPH", "0") == "1"
 depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=1))
+mask, exh = int(os.environ.get("MEAO_HQ_MASK", "0")), os.environ.get("MEAO_EXH", "0") == "1"
 ao = AmbientOcclusion(Camera(W, H), device=0, use_graph=graph)
-orc = Oracle(W, H, threads=8)
+ao.highQualityMask, ao.sampleExhaustively = mask, exh
+orc = Oracle(W, H, threads=8, high_quality_mask=mask, sample_exhaustively=exh)
 ref = orc.run(depth)
 try:
     got = ao.render(torch.from_numpy(depth).cuda())
@@ -18,7 +20,7 @@ try:
 except Exception as e:
     print("render failed:", e); sys.exit(1)
 print("final mismatches", int((got != ref).sum()), "of", got.size)
-for bid in range(1, 18):
+for bid in list(range(1, 18)) + [17 + k for k in range(1, 5) if (mask >> (k - 1)) & 1]:
     g, r = ao.debug_buffer(bid), orc.buffer(bid)
     if g.dtype == np.uint8:
         r = orc.codes(bid); bad = g != r
@@ -32,3 +34,10 @@ for bid in range(1, 18):
         idx = np.argwhere(bad)
         msg = f" first {idx[0].tolist()} got {g[tuple(idx[0])]} ref {r[tuple(idx[0])]}; rows {idx[:,-2].min()}..{idx[:,-2].max()} cols {idx[:,-1].min()}..{idx[:,-1].max()}"
     print(f"  {bid:2d} {ao.DEBUG_NAMES[bid]:18s} mismatches {n:8d} / {g.size}{msg}")
+if os.environ.get("MEAO_VIEWS", "0") == "1":
+    bad = 0
+    for bid in range(1, 18):
+        v = ao.debug_view(bid)
+        ao.synchronize()
+        bad += int((v.cpu().numpy() != orc.debug_view(bid)).sum())
+    print("debug view mismatches", bad)

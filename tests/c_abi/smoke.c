@@ -34,6 +34,16 @@ int main(int argc, char **argv)
         float sum = 0; for (int i = 12; i < 24; i++) sum += rc[i];
         if (sum < 0.999999f || sum > 1.000001f) { fprintf(stderr, "weights do not sum to 1: %g\n", sum); return 1; }
         if (meao_algorithmic_bytes(c, 0) != 131613600LL) return fail("algorithmic bytes", c);
+        /* ABI v2: the undispatched shader variants are plan inputs like the parameters */
+        MeaoVariants v = {0, 1, 12}, back;
+        float rw[28], re[28];
+        if (meao_kernels_per_frame(c) != 9 || meao_set_variants(c, &v) != 1 || meao_set_variants(c, &v) != 0) return fail("set_variants", c);
+        if (meao_get_variants(c, &back) || back.high_quality_mask != 12 || back.sample_exhaustively != 1) return fail("get_variants", c);
+        if (meao_kernels_per_frame(c) != 11 || meao_render_constants(c, 1, re) || meao_render_constants_wide(c, 1, rw)) return fail("variant constants", c);
+        if (!(re[12] > 0.0f) || rc[12] != 0.0f) { fprintf(stderr, "exhaustive mode must keep weight slot 0 (AO.cs:711)\n"); return 1; }
+        if (rw[24] != 1.0f / 1920.0f || re[24] != 1.0f / 480.0f) { fprintf(stderr, "gInvSliceDimension of the tiled / non-tiled source\n"); return 1; }
+        v.high_quality_mask = 16;
+        if (meao_set_variants(c, &v) != MEAO_ERR_INVALID) { fprintf(stderr, "mask 16 must be refused\n"); return 1; }
         float d = 0; uint8_t o = 0;
         if (meao_render_host(c, &d, MEAO_DEPTH_RAW_F32, &o) != MEAO_ERR_CUDA) { fprintf(stderr, "compute on a plan-only context must fail\n"); return 1; }
         meao_destroy(c);

@@ -22,7 +22,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, W, H, q):
+def _worker(rank, world, port, W, H, q, mask=0):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -33,12 +33,13 @@ def _worker(rank, world, port, W, H, q):
     try:
         lin = synth.random_depth(W, H, seed=77)
         depth = synth.lin01_to_raw(lin)
-        ref = Oracle(W, H, intensity=1.1).run(depth)
+        ref = Oracle(W, H, intensity=1.1, high_quality_mask=mask).run(depth)
 
         cuts = rowtile.partition(H, world)
         r0, r1 = cuts[rank], cuts[rank + 1]
         plan = AmbientOcclusion(Camera(W, H), device=-1)        # planning-only context: no GPU needed
         plan.intensity = 1.1
+        plan.highQualityMask = mask
         prev0, next1 = rowtile.neighbours(cuts, rank)
         plan.set_row_band(r0, r1, prev0, next1)
         rows = plan.band_rows()
@@ -46,7 +47,7 @@ def _worker(rank, world, port, W, H, q):
         # this rank only has its band of the depth buffer
         mine = np.full((H, W), 0.5, np.float32)
         mine[r0:r1] = depth[r0:r1]
-        o = Oracle(W, H, intensity=1.1)
+        o = Oracle(W, H, intensity=1.1, high_quality_mask=mask)
         o.downsample(mine)
         low = {k: o.buffer(1 + k) for k in range(1, 5)}
         for k in range(1, 5):                                   # forget everything this band does not own
@@ -73,6 +74,14 @@ def _worker(rank, world, port, W, H, q):
                 o.set_buffer(5 + k, DF.tiled_view(low[k], sw, sh, np.float32(1e5) if k <= 2 else np.float32(0)))
         for k in range(1, 5):
             o.render(k)
+        for k in range(1, 5):                                   # Render.compute kernel "main" reads LowDepth<k> itself (+-8 rows, clamped)
+            if (mask >> (k - 1)) & 1:
+                for kk in range(1, 5):
+                    nlo, nhi = rows["need_low"][kk]
+                    chk = o.buffer(1 + kk)
+                    chk[:nlo] = np.nan
+                    chk[nhi:] = np.nan                              # poison what the planner says is never read
+                o.render_wide(k)
         for lo_level in range(4, 0, -1):
             o.upsample(lo_level)
         got = o.ao_u8()[r0:r1]
@@ -81,13 +90,13 @@ def _worker(rank, world, port, W, H, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,W,H", [(2, 192, 1088), (3, 128, 1584)])
-def test_row_bands_over_gloo_match_full_frame(world, W, H):
+@pytest.mark.parametrize("world,W,H,mask", [(2, 192, 1088, 0), (3, 128, 1584, 0), (2, 192, 1088, 15)])
+def test_row_bands_over_gloo_match_full_frame(world, W, H, mask):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, W, H, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, W, H, q, mask)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
