@@ -169,8 +169,14 @@ __device__ __forceinline__ float2 bilateral2(float2 hd, float2 ha,
     const float2 total = __fadd2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(w0, w1), w2), w3), nfs2);
     const float2 wsum = __fadd2_rn(__ffma2_rn(la3, w3, __ffma2_rn(la2, w2, __ffma2_rn(la1, w1, __fmul2_rn(la0, w0)))), nfs2);
     const float2 num = BLEND ? __fmul2_rn(ha, wsum) : wsum;
+#if !MEAO_UPS_STATIC_GUARD
     ok = ok & in_safe_range(total.x) & in_safe_range(total.y)
             & ((num.x == 0.0f) | in_safe_range(num.x)) & ((num.y == 0.0f) | in_safe_range(num.y));
+#endif
+    // MEAO_UPS_STATIC_GUARD: the host sets fast_div_ok only when tol >= 2^-55 and 2^-52 <= nfs < 2^59 (true for every value in
+    // the component's parameter ranges, AO.cs:20-42).  Once the guard above has passed, every b_i is in [tol, 2^60), so
+    // w_i = c_i / b_i <= 9 / tol, total and wsum lie in [nfs, 16 / tol + nfs] (inside [2^-60, 2^60)) and num = ha * wsum is 0 or
+    // >= nfs / 255 >= 2^-60: the range test of the final division can never fail and is not evaluated per pixel.
     return div2_fast_neg(num, __fmul2_rn(total, m1));
 }
 

@@ -7,6 +7,12 @@
 // atlas padding values itself (see render_ao.cu).
 #pragma once
 
+// Build switch: drop the per-pixel range test of the final division in the packed upsample path when the host has proved
+// it redundant from the two tolerances (blur_upsample.cu, bilateral2).  Shared by the kernel and the planner.
+#ifndef MEAO_UPS_STATIC_GUARD
+#define MEAO_UPS_STATIC_GUARD 0
+#endif
+
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -75,6 +81,7 @@ struct UpsampleArgs {
     int hiw, hih;
     float noise_filter_strength, step_size, blur_tolerance, upsample_tolerance;
     int fast_div_ok;        // upsample_tolerance and noise_filter_strength are positive normals in [2^-60, 2^60)
+                            // (built with MEAO_UPS_STATIC_GUARD: additionally tol >= 2^-55 and 2^-52 <= nfs < 2^59, see blur_upsample.cu)
     int row0, row1;         // output rows (hi level) to produce
 };
 // main_premin / main_premin_blendout (COMBINE_LOWER_RESOLUTIONS): the same arguments plus LoResAO2 = HighQuality<lo>

@@ -30,6 +30,43 @@ __device__ __forceinline__ float linearize(float depth, float zbx, float zby)
     return dist;
 }
 
+// Eight pixels at once (MEAO_PACKED_RCP): the mad of DS1:40 is formed directly in negated form, nt = fma(-zbx, d, -zby) = -t
+// exactly (round-to-nearest is sign-symmetric), all eight range tests feed ONE branch, and the reciprocals run as packed
+// f32x2 (rcp2_fast_neg).  If any element is out of range (inf / NaN / zero / denormal / negative) the group takes the plain
+// per-element path of linearize() -- which recomputes t itself, so signed zeros behave exactly as before.
+template <bool RAW, bool REVERSED>
+__device__ __forceinline__ void linearize8(const float (&v)[8], float zbx, float zby, float (&d)[8])
+{
+    if (!RAW) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) d[e] = v[e];
+        return;
+    }
+    const float2 nzx = make_float2(-zbx, -zbx), nzy = make_float2(-zby, -zby);
+    float2 nt[4];
+    bool ok = true;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        nt[q] = __ffma2_rn(make_float2(v[2 * q], v[2 * q + 1]), nzx, nzy);
+        ok = ok & in_safe_range_neg(nt[q].x) & in_safe_range_neg(nt[q].y);
+    }
+    if (ok) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float2 r = rcp2_fast_neg(nt[q]);
+            d[2 * q] = r.x; d[2 * q + 1] = r.y;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            if (REVERSED) { if (v[e] == 0.0f) d[e] = 1e5f; }   // DS1:41-42
+            else          { if (v[e] == 1.0f) d[e] = 1e5f; }   // DS1:43-44
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) d[e] = linearize<RAW, REVERSED>(v[e], zbx, zby);
+    }
+}
+
 // native depth formats: the camera depth texture read by Blit.shader pass 0 (:48-64) is a D32_FLOAT,
 // D24_UNORM_S8_UINT or D16_UNORM resource; SAMPLE_DEPTH_TEXTURE returns code / (2^n - 1) for the UNORM ones
 // (D3D UNORM -> FLOAT rule: (float)code * (1.0f / (2^n - 1))).
@@ -99,8 +136,12 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_depth_kernel(const Prepa
         if (!rowok[p]) continue;
         const int y = ybase + warp + 8 * p;
         float d[8];
+#if MEAO_PACKED_RCP
+        linearize8<RAW, REVERSED>(v[p], a.zbx, a.zby, d);
+#else
 #pragma unroll
         for (int e = 0; e < 8; e++) d[e] = linearize<RAW, REVERSED>(v[p][e], a.zbx, a.zby);
+#endif
 
         __half *lin = a.lin + (size_t)y * a.lin_pitch + x;
         if (full) {

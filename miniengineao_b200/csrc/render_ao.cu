@@ -197,7 +197,16 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
         if (oy < a.row0 || oy >= a.row1 || ox >= a.lw) continue;
         const float *c = tile + (row + kAp) * kSW + (px + kAp);
         const float2 ctr = *reinterpret_cast<const float2 *>(c);
+#if MEAO_PACKED_RCP
+        float2 inv;                                                            // REN:140, both pixels under one range test
+        {
+            const float2 nctr = __fmul2_rn(ctr, make_float2(-1.0f, -1.0f));
+            if (in_safe_range_neg(nctr.x) & in_safe_range_neg(nctr.y)) inv = rcp2_fast_neg(nctr);
+            else inv = make_float2(1.0f / ctr.x, 1.0f / ctr.y);
+        }
+#else
         const float2 inv = make_float2(rcp_ieee(ctr.x), rcp_ieee(ctr.y));      // REN:140
+#endif
         float2 ao = make_float2(0.0f, 0.0f);                                   // REN:142
         if (!EXH) {
             // REN:162-168 -- the 36-sample checker pattern, in call order
