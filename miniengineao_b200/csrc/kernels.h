@@ -9,6 +9,8 @@
 
 // Build switch: drop the per-pixel range test of the final division in the packed upsample path when the host has proved
 // it redundant from the two tolerances (blur_upsample.cu, bilateral2).  Shared by the kernel and the planner.
+// Measured on B200 and NOT adopted: the 48 guard instructions per 8 pixels disappear, but under the 48-register cap ptxas
+// then spills more (stack 48 -> 80 B, +20 MOV, +19 LDL/STL) and the frame got slower (117.2 vs 119.3 Gpx/s).
 #ifndef MEAO_UPS_STATIC_GUARD
 #define MEAO_UPS_STATIC_GUARD 0
 #endif
