@@ -30,6 +30,8 @@ echo "BEST [$best] $bestv" >> $OUT
 if [ "$best" != "$cur" ]; then
   MEAO_NVCC_DEFS="$best" python miniengineao_b200/build.py --force > /dev/null 2>&1 || echo "rebuild of best failed" >> $OUT
 fi
-python -m pytest tests -m gpu -q --maxfail=5 --tb=short > gpurun_out/pick_best_tests.log 2>&1
-echo "FULL TESTS on [$best]: $(tail -1 gpurun_out/pick_best_tests.log)" >> $OUT
+if [ -z "$SKIP_FULL" ]; then
+  python -m pytest tests -m gpu -q --maxfail=5 --tb=short > gpurun_out/pick_best_tests.log 2>&1
+  echo "FULL TESTS on [$best]: $(tail -1 gpurun_out/pick_best_tests.log)" >> $OUT
+fi
 cat $OUT
