@@ -218,3 +218,36 @@ def test_event_and_composite_pass_selection():
     assert ao.camera_events == ("BeforeReflections", "AfterImageEffects")
     with pytest.raises(ValueError):
         ao.composite(None, color=None)
+
+
+def test_csharp_host_binds_only_declared_entry_points():
+    """host/AmbientOcclusionNative.cs cannot be compiled here (no C# toolchain): at least keep its P/Invoke surface in
+    step with include/meao.h -- every extern it declares must be a declared + exported symbol, with the right arity."""
+    cs = open(os.path.join(ROOT, "host", "AmbientOcclusionNative.cs")).read()
+    externs = re.findall(r"static extern\s+\w+\s+(meao_[a-z0-9_]+)\s*\(([^)]*)\)", cs)
+    assert len(externs) >= 12
+    decl = set(_declared_functions())
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "meao.h")).read(), flags=re.S)
+    for name, args in externs:
+        assert name in decl, f"{name} is bound by the C# host but not declared in include/meao.h"
+        m = re.search(r"\b" + name + r"\s*\(([^)]*)\)", hdr)
+        n_c = 0 if m.group(1).strip() in ("", "void") else m.group(1).count(",") + 1
+        n_cs = 0 if not args.strip() else args.count(",") + 1
+        assert n_c == n_cs, f"{name}: {n_cs} parameters in C#, {n_c} in meao.h"
+    # struct mirrors: field counts of the [StructLayout(Sequential)] twins
+    for struct, n in (("MeaoParams", 7), ("MeaoCamera", 4), ("MeaoDeviceCfg", 2), ("MeaoVariants", 3)):
+        body = re.search(r"public struct " + struct + r"\s*\{(.*?)\}", cs, flags=re.S).group(1)
+        fields = sum(len(d.split(",")) for d in re.findall(r"public\s+(?:float|int|uint)\s+([^;]+);", body))
+        assert fields == n, (struct, fields)
+
+
+def test_csharp_scalar_twin_names_every_oracle_stage():
+    """host/AmbientOcclusionScalar.cs is the (uncompilable here) C# twin of oracle/meao_oracle.c: it must cover the
+    same stage functions and cite them."""
+    cs = open(os.path.join(ROOT, "host", "AmbientOcclusionScalar.cs")).read()
+    for fn in ("meao_oracle_create", "meao_oracle_downsample", "meao_oracle_render", "meao_oracle_upsample", "meao_oracle_run",
+               "meao_oracle_f32_to_f16_bits", "meao_oracle_f16_bits_to_f32"):
+        assert fn in cs, fn
+    for method in ("Downsample", "Render", "Upsample", "Run", "TimeFrames", "Unorm8Code", "SampleThickness"):
+        assert re.search(r"\b" + method + r"\s*\(", cs), method
+    assert "(GI & 9) == 0" in cs            # Downsample1.compute:73 uses the OCTAL literal 011
