@@ -22,11 +22,20 @@ CASES = {
     "random_130x70_params": (130, 70, lambda: synth.random_depth(130, 70, seed=7),
                              dict(intensity=1.2, thickness_modifier=2.0, blur_tolerance=-3.0, upsample_tolerance=-5.0, noise_filter_tolerance=-1.0)),
     "corridor_160x90": (160, 90, lambda: synth.corridor(160, 90), dict(intensity=1.1)),
+    # the shader variants the reference ships but never dispatches: extra key "variants" =
+    # [single_pass_stereo, sample_exhaustively, high_quality_mask], extra buffers 18..21 where selected
+    "variant_exhaustive_101x67": (101, 67, lambda: synth.random_depth(101, 67, seed=5), dict(intensity=1.1, sample_exhaustively=True)),
+    "variant_hq15_exhaustive_118x90": (118, 90, lambda: synth.random_depth(118, 90, seed=6),
+                                       dict(intensity=1.2, thickness_modifier=2.0, high_quality_mask=15, sample_exhaustively=True)),
+    "variant_hq10_corridor_144x80": (144, 80, lambda: synth.corridor(144, 80), dict(high_quality_mask=0b1010)),
 }
 
 
 def main():
+    only_new = "--only-new" in sys.argv       # keep the committed bytes of existing fixtures untouched
     for name, (W, H, gen, kw) in CASES.items():
+        if only_new and os.path.exists(os.path.join(HERE, name + ".npz")):
+            continue
         lin = gen()
         depth = synth.lin01_to_raw(lin)
         o = Oracle(W, H, **kw)
@@ -34,7 +43,10 @@ def main():
         data = {"depth": depth, "ao": ao, "params": np.array([kw.get("noise_filter_tolerance", 0.0), kw.get("blur_tolerance", -4.6),
                                                               kw.get("upsample_tolerance", -12.0), kw.get("thickness_modifier", 1.0),
                                                               kw.get("intensity", 1.0)], np.float32)}
-        for bid in range(1, 18):
+        mask = kw.get("high_quality_mask", 0)
+        if mask or kw.get("sample_exhaustively"):
+            data["variants"] = np.array([0, int(kw.get("sample_exhaustively", False)), mask], np.int32)
+        for bid in list(range(1, 18)) + [17 + k for k in range(1, 5) if (mask >> (k - 1)) & 1]:
             b = o.buffer(bid)
             if bid >= 10:
                 data[f"buf{bid}"] = o.codes(bid)

@@ -206,11 +206,13 @@ def test_oracle_reproduces_golden_fixture(path):
     g = np.load(path)
     H, W = g["depth"].shape
     p = g["params"]
+    v = g["variants"] if "variants" in g.files else np.zeros(3, np.int32)
     o = Oracle(W, H, noise_filter_tolerance=float(p[0]), blur_tolerance=float(p[1]), upsample_tolerance=float(p[2]),
-               thickness_modifier=float(p[3]), intensity=float(p[4]))
+               thickness_modifier=float(p[3]), intensity=float(p[4]),
+               single_pass_stereo=bool(v[0]), sample_exhaustively=bool(v[1]), high_quality_mask=int(v[2]))
     ao = o.run(g["depth"])
     assert np.array_equal(ao, g["ao"])
-    for bid in range(1, 18):
+    for bid in [int(k[3:]) for k in g.files if k.startswith("buf")]:
         ref = g[f"buf{bid}"]
         if ref.dtype == np.uint8:
             assert np.array_equal(o.codes(bid), ref), bid
