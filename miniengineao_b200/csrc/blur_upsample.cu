@@ -201,21 +201,21 @@ cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensor
     const int t = use_tma ? 1 : 0;
     if (!lo_ao2) {
         if (a.hi_ao) {
-            if (a.hi_is_half) blur_upsample_kernel<true, true><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, a, t);
-            else              blur_upsample_kernel<true, false><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, a, t);
+            if (a.hi_is_half) MEAO_LAUNCH((blur_upsample_kernel<true, true>), grid, kThreads, 0, s, lo_depth_map, lo_ao_map, a, t);
+            else              MEAO_LAUNCH((blur_upsample_kernel<true, false>), grid, kThreads, 0, s, lo_depth_map, lo_ao_map, a, t);
         } else {
-            if (a.hi_is_half) blur_upsample_kernel<false, true><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, a, t);
-            else              blur_upsample_kernel<false, false><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, a, t);
+            if (a.hi_is_half) MEAO_LAUNCH((blur_upsample_kernel<false, true>), grid, kThreads, 0, s, lo_depth_map, lo_ao_map, a, t);
+            else              MEAO_LAUNCH((blur_upsample_kernel<false, false>), grid, kThreads, 0, s, lo_depth_map, lo_ao_map, a, t);
         }
     } else {        // main_premin / main_premin_blendout
         if (!lo_ao2_map) return cudaErrorInvalidValue;
         const UpsamplePreminArgs pa{a, lo_ao2, lo_a2pitch};
         if (a.hi_ao) {
-            if (a.hi_is_half) blur_upsample_premin_kernel<true, true><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, *lo_ao2_map, pa, t);
-            else              blur_upsample_premin_kernel<true, false><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, *lo_ao2_map, pa, t);
+            if (a.hi_is_half) MEAO_LAUNCH((blur_upsample_premin_kernel<true, true>), grid, kThreads, 0, s, lo_depth_map, lo_ao_map, *lo_ao2_map, pa, t);
+            else              MEAO_LAUNCH((blur_upsample_premin_kernel<true, false>), grid, kThreads, 0, s, lo_depth_map, lo_ao_map, *lo_ao2_map, pa, t);
         } else {
-            if (a.hi_is_half) blur_upsample_premin_kernel<false, true><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, *lo_ao2_map, pa, t);
-            else              blur_upsample_premin_kernel<false, false><<<grid, kThreads, 0, s>>>(lo_depth_map, lo_ao_map, *lo_ao2_map, pa, t);
+            if (a.hi_is_half) MEAO_LAUNCH((blur_upsample_premin_kernel<false, true>), grid, kThreads, 0, s, lo_depth_map, lo_ao_map, *lo_ao2_map, pa, t);
+            else              MEAO_LAUNCH((blur_upsample_premin_kernel<false, false>), grid, kThreads, 0, s, lo_depth_map, lo_ao_map, *lo_ao2_map, pa, t);
         }
     }
     return cudaGetLastError();

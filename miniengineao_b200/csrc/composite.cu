@@ -92,8 +92,8 @@ cudaError_t launch_composite(const uint8_t *ao, void *color, long long npix, int
     if (npix <= 0) return cudaSuccess;
     const long long groups = (npix + 3) / 4;
     const unsigned blocks = (unsigned)((groups + kCompThreads - 1) / kCompThreads);
-    if (half) composite_kernel<true><<<blocks, kCompThreads, 0, s>>>(ao, color, npix, rgb, alpha, one_minus);
-    else      composite_kernel<false><<<blocks, kCompThreads, 0, s>>>(ao, color, npix, rgb, alpha, one_minus);
+    if (half) MEAO_LAUNCH((composite_kernel<true>), blocks, kCompThreads, 0, s, ao, color, npix, rgb, alpha, one_minus);
+    else      MEAO_LAUNCH((composite_kernel<false>), blocks, kCompThreads, 0, s, ao, color, npix, rgb, alpha, one_minus);
     return cudaGetLastError();
 }
 

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) debug_view_kernel(const DebugViewArgs a)
 cudaError_t launch_debug_view(const DebugViewArgs &a, cudaStream_t s)
 {
     dim3 grid(ceil_div(a.W, 256), a.H);
-    debug_view_kernel<<<grid, 256, 0, s>>>(a);
+    MEAO_LAUNCH((debug_view_kernel), grid, 256, 0, s, a);
     return cudaGetLastError();
 }
 

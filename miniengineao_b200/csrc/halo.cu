@@ -28,7 +28,7 @@ cudaError_t launch_halo_copy(const HaloArgs &a, cudaStream_t s)
     int maxn = 0;
     for (int i = 0; i < a.nseg; i++) maxn = max(maxn, a.seg[i].rows * a.seg[i].width);
     dim3 grid(min(ceil_div(maxn, 256), 64), a.nseg);
-    halo_copy_kernel<<<grid, 256, 0, s>>>(a);
+    MEAO_LAUNCH((halo_copy_kernel), grid, 256, 0, s, a);
     return cudaGetLastError();
 }
 

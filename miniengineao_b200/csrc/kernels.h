@@ -15,10 +15,23 @@
 #define MEAO_UPS_STATIC_GUARD 0
 #endif
 
+#ifdef MEAO_EMULATE              // tests/emu only (see common.cuh)
+#include "cuda_emu.h"
+#else
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
+
+// Kernel launch.  `k` is the kernel name IN PARENTHESES (they protect the commas of template arguments from the
+// preprocessor); in the CUDA build the macro expands to exactly  kernel<...><<<grid, block, smem, stream>>>(args).
+#define MEAO_UNPAREN(...) __VA_ARGS__
+#ifdef MEAO_EMULATE
+#define MEAO_LAUNCH(k, grid, block, smem, stream, ...) meao_emu::launch((grid), (block), (smem), [&]() { MEAO_UNPAREN k(__VA_ARGS__); })
+#else
+#define MEAO_LAUNCH(k, grid, block, smem, stream, ...) MEAO_UNPAREN k<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
 
 namespace meao {
 

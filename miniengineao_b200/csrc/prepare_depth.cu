@@ -189,16 +189,16 @@ cudaError_t launch_prepare_depth(const PrepareArgs &a, cudaStream_t s)
     if (a.row1 <= a.row0) return cudaSuccess;
     dim3 grid(ceil_div(a.W, kPrepTileW), ceil_div(a.row1 - a.row0, kPrepTileH));
     if (!a.raw) {
-        prepare_depth_kernel<false, true, IN_F32><<<grid, kPrepThreads, 0, s>>>(a);
+        MEAO_LAUNCH((prepare_depth_kernel<false, true, IN_F32>), grid, kPrepThreads, 0, s, a);
     } else if (a.in_format == IN_D16) {
-        if (a.reversed_z) prepare_depth_kernel<true, true, IN_D16><<<grid, kPrepThreads, 0, s>>>(a);
-        else              prepare_depth_kernel<true, false, IN_D16><<<grid, kPrepThreads, 0, s>>>(a);
+        if (a.reversed_z) MEAO_LAUNCH((prepare_depth_kernel<true, true, IN_D16>), grid, kPrepThreads, 0, s, a);
+        else              MEAO_LAUNCH((prepare_depth_kernel<true, false, IN_D16>), grid, kPrepThreads, 0, s, a);
     } else if (a.in_format == IN_D24S8) {
-        if (a.reversed_z) prepare_depth_kernel<true, true, IN_D24S8><<<grid, kPrepThreads, 0, s>>>(a);
-        else              prepare_depth_kernel<true, false, IN_D24S8><<<grid, kPrepThreads, 0, s>>>(a);
+        if (a.reversed_z) MEAO_LAUNCH((prepare_depth_kernel<true, true, IN_D24S8>), grid, kPrepThreads, 0, s, a);
+        else              MEAO_LAUNCH((prepare_depth_kernel<true, false, IN_D24S8>), grid, kPrepThreads, 0, s, a);
     } else {
-        if (a.reversed_z) prepare_depth_kernel<true, true, IN_F32><<<grid, kPrepThreads, 0, s>>>(a);
-        else              prepare_depth_kernel<true, false, IN_F32><<<grid, kPrepThreads, 0, s>>>(a);
+        if (a.reversed_z) MEAO_LAUNCH((prepare_depth_kernel<true, true, IN_F32>), grid, kPrepThreads, 0, s, a);
+        else              MEAO_LAUNCH((prepare_depth_kernel<true, false, IN_F32>), grid, kPrepThreads, 0, s, a);
     }
     return cudaGetLastError();
 }

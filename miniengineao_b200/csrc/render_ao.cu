@@ -134,7 +134,11 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
 {
 #ifdef MEAO_DEVICE_OK
     constexpr int kAp = Geo<MODE>::kAp, kSW = Geo<MODE>::kSW, kSH = Geo<MODE>::kSH;
+#ifdef MEAO_EMULATE
+    float *tile = reinterpret_cast<float *>(meao_emu::dynamic_smem());
+#else
     extern __shared__ __align__(128) float tile[];     // kSW * kSH floats
+#endif
     __shared__ __align__(8) uint64_t bar;
 
     const int tid = threadIdx.x;
@@ -264,12 +268,12 @@ cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const Ren
     const int t = use_tma ? 1 : 0;
     if (!a.wide) {
         const size_t smem = (size_t)Geo<0>::kSW * Geo<0>::kSH * sizeof(float);
-        if (!a.exhaustive) render_ao_kernel<0, false><<<grid, kThreads, smem, s>>>(low_map, a, t);
-        else               render_ao_kernel<0, true><<<grid, kThreads, smem, s>>>(low_map, a, t);
+        if (!a.exhaustive) MEAO_LAUNCH((render_ao_kernel<0, false>), grid, kThreads, smem, s, low_map, a, t);
+        else               MEAO_LAUNCH((render_ao_kernel<0, true>), grid, kThreads, smem, s, low_map, a, t);
     } else {
         const size_t smem = (size_t)Geo<1>::kSW * Geo<1>::kSH * sizeof(float);
-        if (!a.exhaustive) render_ao_kernel<1, false><<<grid, kThreads, smem, s>>>(low_map, a, t);
-        else               render_ao_kernel<1, true><<<grid, kThreads, smem, s>>>(low_map, a, t);
+        if (!a.exhaustive) MEAO_LAUNCH((render_ao_kernel<1, false>), grid, kThreads, smem, s, low_map, a, t);
+        else               MEAO_LAUNCH((render_ao_kernel<1, true>), grid, kThreads, smem, s, low_map, a, t);
     }
     return cudaGetLastError();
 }
@@ -278,7 +282,7 @@ cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int
                                __half *out, cudaStream_t s)
 {
     dim3 grid(ceil_div(sw, 128), sh, 16);
-    synth_tiled_kernel<<<grid, 128, 0, s>>>(low, lw, lh, lpitch, sw, sh, pad, out);
+    MEAO_LAUNCH((synth_tiled_kernel), grid, 128, 0, s, low, lw, lh, lpitch, sw, sh, pad, out);
     return cudaGetLastError();
 }
 

@@ -54,7 +54,7 @@ cudaError_t launch_selftest_div(uint64_t n, uint32_t seed, unsigned long long *m
 {
     const int blocks = 148 * 8, threads = 256;
     const uint64_t per = (n + (uint64_t)blocks * threads - 1) / ((uint64_t)blocks * threads);
-    selftest_div_kernel<<<blocks, threads, 0, s>>>(per, seed, mismatch_dev);
+    MEAO_LAUNCH((selftest_div_kernel), blocks, threads, 0, s, per, seed, mismatch_dev);
     return cudaGetLastError();
 }
 

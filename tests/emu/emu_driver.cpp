@@ -1,0 +1,188 @@
+// emu_driver.cpp -- runs one frame through the HOST-compiled kernel sources (TEST INFRASTRUCTURE ONLY, see cuda_emu.h).
+// It owns pitched buffers laid out like MeaoCtx's arena and fills PrepareArgs / RenderArgs / UpsampleArgs the way
+// meao_api.cu's record_downsample / record_render / record_upsample do; the per-dispatch constants are handed in by the
+// test (which reads them from a plan-only libmeao context), so the planner itself is not duplicated here.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../miniengineao_b200/csrc/common.cuh"
+#include "../../miniengineao_b200/csrc/kernels.h"
+
+using namespace meao;
+
+namespace {
+
+inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+template <class T> T *alloc(size_t n) { void *p = nullptr; if (posix_memalign(&p, 256, (n * sizeof(T) + 255) / 256 * 256 + 256)) abort(); memset(p, 0, n * sizeof(T)); return (T *)p; }
+
+struct Emu {
+    int W, H, lw[7], lh[7];
+    __half *lin; int lin_pitch;
+    float *low[5]; int low_pitch[5];
+    uint8_t *occ[5], *comb[4], *hq[5]; int occ_pitch[5];
+    uint8_t *result; int result_pitch;
+    // constants (set by emu_set_constants)
+    float zbx = 0, zby = 1; int raw = 1, reversed_z = 1;
+    float inv_thickness[5][12], inv_thickness_wide[5][12], sample_weight[5][12];
+    float reject_fadeoff = -1, intensity = 1, pad[5] = {0, 0, 0, 0, 0};
+    float nfs[5], step[5], kblur[5], tol[5];
+    int hq_mask = 0, exhaustive = 0;
+};
+
+}  // namespace
+
+extern "C" {
+
+void *emu_create(int W, int H)
+{
+    Emu *e = new Emu();
+    e->W = W; e->H = H;
+    for (int l = 0; l < 7; l++) { const int d = 1 << l; e->lw[l] = (W + d - 1) / d; e->lh[l] = (H + d - 1) / d; }
+    e->lin_pitch = align_up(W, 64); e->lin = alloc<__half>((size_t)e->lin_pitch * H);
+    e->result_pitch = align_up(W, 128); e->result = alloc<uint8_t>((size_t)e->result_pitch * H);
+    for (int k = 1; k <= 4; k++) {
+        e->low_pitch[k] = align_up(e->lw[k], 32); e->occ_pitch[k] = align_up(e->lw[k], 128);
+        e->low[k] = alloc<float>((size_t)e->low_pitch[k] * e->lh[k]);
+        e->occ[k] = alloc<uint8_t>((size_t)e->occ_pitch[k] * e->lh[k]);
+        e->hq[k] = alloc<uint8_t>((size_t)e->occ_pitch[k] * e->lh[k]);
+        if (k <= 3) e->comb[k] = alloc<uint8_t>((size_t)e->occ_pitch[k] * e->lh[k]);
+    }
+    return e;
+}
+
+void emu_destroy(void *h)
+{
+    Emu *e = (Emu *)h;
+    free(e->lin); free(e->result);
+    for (int k = 1; k <= 4; k++) { free(e->low[k]); free(e->occ[k]); free(e->hq[k]); if (k <= 3) free(e->comb[k]); }
+    delete e;
+}
+
+// rc[k], rcw[k]: the 28 floats of meao_render_constants / meao_render_constants_wide (k = 1..4 at index k-1);
+// uc[lo]: the 8 floats of meao_upsample_constants; zb: ZBufferParams; pad12: value of the DS1-written atlas padding texels
+void emu_set_constants(void *h, const float *rc, const float *rcw, const float *uc, const float *zb, float pad12,
+                       int raw, int reversed_z, int hq_mask, int exhaustive)
+{
+    Emu *e = (Emu *)h;
+    for (int k = 1; k <= 4; k++) {
+        memcpy(e->inv_thickness[k], rc + 28 * (k - 1), 48);
+        memcpy(e->sample_weight[k], rc + 28 * (k - 1) + 12, 48);
+        memcpy(e->inv_thickness_wide[k], rcw + 28 * (k - 1), 48);
+        e->pad[k] = (k <= 2) ? pad12 : 0.0f;
+        const float *u = uc + 8 * (k - 1);
+        e->nfs[k] = u[4]; e->step[k] = u[5]; e->kblur[k] = u[6]; e->tol[k] = u[7];
+    }
+    e->reject_fadeoff = rc[26]; e->intensity = rc[27];
+    e->zbx = zb[0]; e->zby = zb[1]; e->raw = raw; e->reversed_z = reversed_z; e->hq_mask = hq_mask; e->exhaustive = exhaustive;
+}
+
+static void run_downsample(Emu *e, const void *depth, int in_format)
+{
+    PrepareArgs a{};
+    a.depth = depth; a.in_format = in_format; a.W = e->W; a.H = e->H; a.depth_row0 = 0; a.row0 = 0; a.row1 = e->H;
+    a.lin = e->lin; a.lin_pitch = e->lin_pitch;
+    for (int k = 1; k <= 4; k++) { a.low[k - 1] = e->low[k]; a.low_pitch[k - 1] = e->low_pitch[k]; }
+    a.zbx = e->zbx; a.zby = e->zby; a.raw = e->raw; a.reversed_z = e->reversed_z;
+    a.vec_ok = (((uintptr_t)depth & 15) == 0) && (e->W % (in_format == 1 ? 8 : 4) == 0);
+    launch_prepare_depth(a, nullptr);
+}
+
+static void run_render(Emu *e, int k, bool wide)
+{
+    static const int idx_checker[7] = {1, 3, 4, 8, 11, 6, 10}, idx_exh[12] = {0, 1, 2, 3, 4, 8, 11, 5, 6, 7, 9, 10};
+    const int n = e->exhaustive ? 12 : 7; const int *idx = e->exhaustive ? idx_exh : idx_checker;
+    RenderArgs a{};
+    a.low = e->low[k]; a.lw = e->lw[k]; a.lh = e->lh[k]; a.lpitch = e->low_pitch[k];
+    a.occ = wide ? e->hq[k] : e->occ[k]; a.opitch = e->occ_pitch[k];
+    a.sw = e->lw[k + 2]; a.sh = e->lh[k + 2];
+    a.pad = __half2float(__float2half_rn(e->pad[k]));
+    const float *it = wide ? e->inv_thickness_wide[k] : e->inv_thickness[k];
+    for (int i = 0; i < n; i++) { a.inv_thickness[i] = it[idx[i]]; a.neg_front[i] = -(a.inv_thickness[i] - 0.5f); a.weight[i] = e->sample_weight[k][idx[i]]; }
+    a.reject_fadeoff = e->reject_fadeoff; a.intensity = e->intensity;
+    a.row0 = 0; a.row1 = e->lh[k]; a.wide = wide; a.exhaustive = e->exhaustive;
+    CUtensorMap dummy{};
+    launch_render_ao(dummy, false, a, nullptr);
+}
+
+static void run_upsample(Emu *e, int lo)
+{
+    const int hi = lo - 1;
+    UpsampleArgs a{};
+    a.lo_depth = e->low[lo]; a.low = e->lw[lo]; a.loh = e->lh[lo]; a.lo_dpitch = e->low_pitch[lo];
+    a.lo_ao = (lo == 4) ? e->occ[4] : e->comb[lo]; a.lo_apitch = e->occ_pitch[lo];
+    if (hi == 0) { a.hi_depth = e->lin; a.hi_is_half = 1; a.hi_dpitch = e->lin_pitch; a.hi_ao = nullptr; a.out = e->result; a.out_pitch = e->result_pitch; }
+    else { a.hi_depth = e->low[hi]; a.hi_is_half = 0; a.hi_dpitch = e->low_pitch[hi]; a.hi_ao = e->occ[hi]; a.hi_apitch = e->occ_pitch[hi]; a.out = e->comb[hi]; a.out_pitch = e->occ_pitch[hi]; }
+    a.out_row_origin = 0; a.out_vec_ok = 1;
+    a.hiw = e->lw[hi]; a.hih = e->lh[hi];
+    a.noise_filter_strength = e->nfs[lo]; a.step_size = e->step[lo]; a.blur_tolerance = e->kblur[lo]; a.upsample_tolerance = e->tol[lo];
+    auto safe = [](float x) { return x >= 8.673617379884035e-19f && x < 1152921504606846976.0f; };
+    a.fast_div_ok = safe(a.upsample_tolerance) && safe(a.noise_filter_strength);
+#if MEAO_UPS_STATIC_GUARD
+    a.fast_div_ok = a.fast_div_ok && a.upsample_tolerance >= 2.7755575615628914e-17f && a.noise_filter_strength >= 2.220446049250313e-16f &&
+                    a.noise_filter_strength < 576460752303423488.0f;
+#endif
+    a.row0 = 0; a.row1 = e->lh[hi];
+    const bool premin = ((e->hq_mask >> (lo - 1)) & 1) != 0;
+    CUtensorMap dummy{};
+    launch_blur_upsample(dummy, dummy, &dummy, false, a, premin ? e->hq[lo] : nullptr, e->occ_pitch[lo], nullptr);
+}
+
+// in_format: 0 = f32, 1 = D16 codes, 2 = D24S8 words (PrepareArgs.in_format); depth must be 16-byte aligned
+void emu_run(void *h, const void *depth, int in_format)
+{
+    Emu *e = (Emu *)h;
+    run_downsample(e, depth, in_format);
+    for (int k = 1; k <= 4; k++) run_render(e, k, false);
+    for (int k = 1; k <= 4; k++) if ((e->hq_mask >> (k - 1)) & 1) run_render(e, k, true);
+    for (int lo = 4; lo >= 1; lo--) run_upsample(e, lo);
+}
+
+// buffer <id> (1..21) in the reference layout / native type, like meao_get_buffer
+int emu_get_buffer(void *h, int id, void *out)
+{
+    Emu *e = (Emu *)h;
+    auto copy2d = [&](const void *src, size_t pitch_bytes, int w, int hgt, int elem) {
+        for (int y = 0; y < hgt; y++) memcpy((char *)out + (size_t)y * w * elem, (const char *)src + (size_t)y * pitch_bytes, (size_t)w * elem);
+    };
+    if (id == 1) copy2d(e->lin, (size_t)e->lin_pitch * 2, e->lw[0], e->lh[0], 2);
+    else if (id >= 2 && id <= 5) copy2d(e->low[id - 1], (size_t)e->low_pitch[id - 1] * 4, e->lw[id - 1], e->lh[id - 1], 4);
+    else if (id >= 6 && id <= 9) {
+        const int k = id - 5;
+        launch_synth_tiled(e->low[k], e->lw[k], e->lh[k], e->low_pitch[k], e->lw[k + 2], e->lh[k + 2], __half2float(__float2half_rn(e->pad[k])), (__half *)out, nullptr);
+    }
+    else if (id >= 10 && id <= 13) copy2d(e->occ[id - 9], e->occ_pitch[id - 9], e->lw[id - 9], e->lh[id - 9], 1);
+    else if (id >= 14 && id <= 16) copy2d(e->comb[id - 13], e->occ_pitch[id - 13], e->lw[id - 13], e->lh[id - 13], 1);
+    else if (id == 17) copy2d(e->result, e->result_pitch, e->lw[0], e->lh[0], 1);
+    else if (id >= 18 && id <= 21) copy2d(e->hq[id - 17], e->occ_pitch[id - 17], e->lw[id - 17], e->lh[id - 17], 1);
+    else return -1;
+    return 0;
+}
+
+// the debug view of buffer <id> (meao_debug_view) into out[W * H]
+int emu_debug_view(void *h, int id, uint8_t *out)
+{
+    Emu *e = (Emu *)h;
+    DebugViewArgs a{};
+    a.W = e->W; a.H = e->H; a.out = out; a.out_pitch = e->W;
+    if (id >= 6 && id <= 9) {
+        const int k = id - 5;
+        a.tiled = 1; a.src = e->low[k]; a.elem = 4; a.spitch = e->low_pitch[k]; a.sw = e->lw[k + 2]; a.sh = e->lh[k + 2]; a.lw = e->lw[k]; a.lh = e->lh[k];
+        a.pad = __half2float(__float2half_rn(e->pad[k]));
+    } else if (id == 1) { a.src = e->lin; a.elem = 2; a.spitch = e->lin_pitch; a.sw = e->lw[0]; a.sh = e->lh[0]; }
+    else if (id >= 2 && id <= 5) { a.src = e->low[id - 1]; a.elem = 4; a.spitch = e->low_pitch[id - 1]; a.sw = e->lw[id - 1]; a.sh = e->lh[id - 1]; }
+    else if (id >= 10 && id <= 13) { a.src = e->occ[id - 9]; a.elem = 1; a.spitch = e->occ_pitch[id - 9]; a.sw = e->lw[id - 9]; a.sh = e->lh[id - 9]; }
+    else if (id >= 14 && id <= 16) { a.src = e->comb[id - 13]; a.elem = 1; a.spitch = e->occ_pitch[id - 13]; a.sw = e->lw[id - 13]; a.sh = e->lh[id - 13]; }
+    else if (id == 17) { a.src = e->result; a.elem = 1; a.spitch = e->result_pitch; a.sw = e->lw[0]; a.sh = e->lh[0]; }
+    else return -1;
+    launch_debug_view(a, nullptr);
+    return 0;
+}
+
+// Blit.shader passes 1 / 2 on host buffers (launch_composite): color updated in place
+void emu_composite(const uint8_t *ao, void *color, long long npix, int half, int rgb, int alpha, int one_minus)
+{
+    launch_composite(ao, color, npix, half, rgb, alpha, one_minus, nullptr);
+}
+
+}  // extern "C"

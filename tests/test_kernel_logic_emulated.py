@@ -1,0 +1,144 @@
+"""CPU tests of the CUDA KERNEL SOURCES: miniengineao_b200/csrc/*.cu compiled by g++ for the host (tests/emu, -DMEAO_EMULATE,
+one fiber per CUDA thread, fibers switch at __syncthreads) and run against the oracle, bit for bit, without a GPU.
+
+What this proves: the kernels' logic -- tiling, aprons, border / padding handling, operation order, packed-lane bookkeeping,
+the variants' plumbing, every build switch -- is the reference's arithmetic.  What it cannot prove: anything about the real
+hardware path (TMA boxes, MUFU.RCP + refinement, memory model); that is what tests/test_parity_gpu.py does on the B200.
+The emulator is test infrastructure: libmeao.so never contains it and still has no CPU path (test_abi.py).
+"""
+import numpy as np
+import pytest
+
+from miniengineao_b200 import AmbientOcclusion, Camera, synth
+from oracle import oracle as O
+from oracle.oracle import Oracle
+
+from emu.emu import EmulatedFrame, composite  # noqa: E402  (tests/ is on sys.path via conftest)
+
+
+def _plan(W, H, **kw):
+    cam = Camera(W, H, usesReversedZBuffer=kw.get("reversed_z", True))
+    p = AmbientOcclusion(cam, device=-1)
+    for py, cs in (("noise_filter_tolerance", "noiseFilterTolerance"), ("blur_tolerance", "blurTolerance"), ("upsample_tolerance", "upsampleTolerance"),
+                   ("thickness_modifier", "thicknessModifier"), ("intensity", "intensity"), ("sample_exhaustively", "sampleExhaustively"),
+                   ("high_quality_mask", "highQualityMask")):
+        if py in kw:
+            setattr(p, cs, kw[py])
+    return p
+
+
+def _compare_all(f, orc, tag, mask=0):
+    bad = []
+    for bid in list(range(1, 18)) + [17 + k for k in range(1, 5) if (mask >> (k - 1)) & 1]:
+        got, ref = f.buffer(bid), orc.buffer(bid)
+        if got.dtype == np.uint8:
+            n = int((got != orc.codes(bid)).sum())
+        elif got.dtype == np.float16:
+            with np.errstate(over="ignore"):
+                n = int((got.view(np.uint16) != ref.astype(np.float16).view(np.uint16)).sum())
+        else:
+            n = int((got.view(np.uint32) != ref.view(np.uint32)).sum())
+        if n:
+            bad.append((bid, n, got.size))
+    assert not bad, f"{tag}: mismatching buffers (id, #diff, size): {bad}"
+
+
+def _run(W, H, seed=1, defs=(), depth=None, **kw):
+    okw = {k: v for k, v in kw.items()}
+    orc = Oracle(W, H, threads=4, **okw)
+    if depth is None:
+        depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=seed), reversed_z=kw.get("reversed_z", True))
+    ref = orc.run(depth)
+    f = EmulatedFrame(_plan(W, H, **kw), defs=tuple(defs))
+    got = f.run(depth)
+    assert int((got != ref).sum()) == 0, (W, H, kw, defs)
+    _compare_all(f, orc, f"{W}x{H} {kw} {defs}", kw.get("high_quality_mask", 0))
+    return f, orc
+
+
+@pytest.mark.parametrize("W,H", [(256, 256), (64, 64), (16, 16), (1, 1), (3, 5), (130, 70), (250, 131), (321, 203), (37, 300), (300, 37)])
+def test_reference_path_all_buffers(W, H):
+    _run(W, H, seed=W * 7 + H, intensity=1.1)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(intensity=0.0), dict(intensity=2.0), dict(thickness_modifier=10.0), dict(blur_tolerance=-1.0), dict(blur_tolerance=-8.0),
+    dict(upsample_tolerance=-1.0), dict(upsample_tolerance=-6.0, noise_filter_tolerance=-8.0), dict(reversed_z=False),
+    dict(noise_filter_tolerance=-3.0, blur_tolerance=-3.0, upsample_tolerance=-4.0, thickness_modifier=4.0, intensity=0.7),
+])
+def test_parameter_sweep(kw):
+    _run(194, 110, seed=11, **kw)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(sample_exhaustively=True), dict(high_quality_mask=15), dict(high_quality_mask=0b0110, sample_exhaustively=True, intensity=1.3),
+    dict(high_quality_mask=0b1001, reversed_z=False),
+])
+@pytest.mark.parametrize("W,H", [(130, 70), (201, 155)])
+def test_shader_variants(W, H, kw):
+    _run(W, H, seed=5, **kw)
+
+
+def test_sky_pixels_take_the_ieee_fallbacks():
+    """Raw depth 0 -> 1e5 -> inf in f16 -> NaN in the sampler; grouped range tests must fall back for the whole group."""
+    W, H = 200, 120
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=5))
+    depth[20:60, 30:90] = 0.0
+    depth[::17, ::13] = 0.0
+    _run(W, H, depth=depth)
+    _run(W, H, depth=depth, high_quality_mask=15, sample_exhaustively=True)
+
+
+def test_corridor_640x360():
+    _run(640, 360, depth=synth.lin01_to_raw(synth.corridor(640, 360)), intensity=1.1)
+
+
+def test_linear_and_native_depth_ingest():
+    W, H = 250, 131
+    lin = synth.random_depth(W, H, seed=9)
+    orc = Oracle(W, H, depth_is_linear=True)
+    ref = orc.run(lin)
+    f = EmulatedFrame(_plan(W, H), linear=True)
+    assert np.array_equal(f.run(lin), ref)
+    _compare_all(f, orc, "linear ingest")
+    raw = synth.lin01_to_raw(lin).astype(np.float64)
+    for bits, dt in ((16, np.uint16), (24, np.uint32)):
+        full = (1 << bits) - 1
+        codes = np.clip(np.rint(raw * full), 1, full).astype(np.uint32)
+        as_float = (codes.astype(np.float32) * np.float32(1.0 / full)).astype(np.float32)
+        orc = Oracle(W, H)
+        ref = orc.run(as_float)
+        words = codes.astype(np.uint16) if bits == 16 else (codes | (np.uint32(0xA5) << np.uint32(24)))
+        f = EmulatedFrame(_plan(W, H))
+        assert np.array_equal(f.run(words.astype(dt)), ref), bits
+        _compare_all(f, orc, f"D{bits}")
+
+
+def test_debug_views():
+    W, H = 130, 70
+    f, orc = _run(W, H, seed=4, high_quality_mask=0b0101)
+    for bid in range(1, 18):
+        assert np.array_equal(f.debug_view(bid), orc.debug_view(bid)), bid
+
+
+def test_composite_passes():
+    rng = np.random.default_rng(0)
+    ao = rng.integers(0, 256, size=(45, 67), dtype=np.uint8)
+    c8 = rng.integers(0, 256, size=(45, 67, 4), dtype=np.uint8)
+    c16 = (rng.uniform(0, 4, size=(45, 67, 4)) ** 3).astype(np.float16)
+    for col in (c8, c16):
+        assert np.array_equal(composite(ao, col, rgb=True, alpha=True, one_minus=False).view(np.uint8), O.composite_framebuffer(ao, col).view(np.uint8))
+        g0, g3 = O.composite_gbuffer(ao, c8, col)
+        assert np.array_equal(composite(ao, c8, rgb=False, alpha=True, one_minus=True), g0)
+        assert np.array_equal(composite(ao, col, rgb=True, alpha=False, one_minus=True).view(np.uint8), g3.view(np.uint8))
+
+
+@pytest.mark.parametrize("defs", [
+    ("-DMEAO_PACKED_RCP=0",), ("-DMEAO_UPS_STATIC_GUARD=1",), ("-DMEAO_REN_CLAMP_MODE=0",), ("-DMEAO_REN_CLAMP_MODE=2",),
+])
+def test_build_switches_keep_the_arithmetic(defs):
+    """Every tuning switch of the kernels (csrc/common.cuh, kernels.h, render_ao.cu) must leave all results unchanged."""
+    _run(161, 93, seed=21, defs=defs, intensity=1.2)
+    depth = synth.lin01_to_raw(synth.random_depth(120, 80, seed=2))
+    depth[10:30, 15:60] = 0.0
+    _run(120, 80, depth=depth, defs=defs, high_quality_mask=15)
