@@ -8,8 +8,8 @@
 //
 // What is and is not emulated: fp32 arithmetic is IEEE on both sides, so results are bit-comparable; MUFU.RCP is replaced
 // by the correctly rounded reciprocal (the refinement steps that follow make the quotient exact from any start within an
-// ulp or two -- on the GPU that is what meao_selftest_div proves for the real MUFU); TMA / mbarrier are not emulated (the
-// emulator always takes the kernels' gather path, use_tma = 0); timing, occupancy and memory behaviour mean nothing here.
+// ulp or two -- on the GPU that is what meao_selftest_div proves for the real MUFU); TMA box loads are emulated as synchronous copies with
+// zero fill (mbarriers become no-ops), so both the TMA path and the gather path of every kernel can be run; timing, occupancy and memory behaviour mean nothing here.
 #pragma once
 
 #include <cmath>
@@ -48,7 +48,8 @@ typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-struct alignas(64) CUtensorMap { uint64_t opaque[16]; };
+// a 2-D tiled tensor map, reduced to what cp.async.bulk.tensor.2d needs (cuTensorMapEncodeTiled's arguments)
+struct alignas(64) CUtensorMap { const void *base; int elem, w, h; size_t pitch_bytes; int bw, bh; uint64_t pad_[3]; };
 
 // ---- built-in variables + the fiber scheduler (tests/emu/emu_runtime.cpp) -------------------------------------------------------
 extern uint3 threadIdx, blockIdx;
@@ -58,6 +59,7 @@ void launch(dim3 grid, dim3 block, size_t dynamic_smem_bytes, const std::functio
 void syncthreads();
 void *dynamic_smem();
 [[noreturn]] void unsupported(const char *what);
+extern long long tma_box_loads;      // number of emulated cp.async.bulk.tensor loads so far (tests assert the TMA branch really ran)
 }
 inline void __syncthreads() { meao_emu::syncthreads(); }
 
@@ -87,4 +89,20 @@ inline float2 __fadd2_rn(float2 a, float2 b) { return float2{__fadd_rn(a.x, b.x)
 
 namespace meao_emu {
 inline float rcp_approx(float x) { return (float)(1.0 / (double)x); }
+// cp.async.bulk.tensor.2d (tiled, no swizzle): box whose first element is (x, y); out-of-bounds elements are zero-filled.
+// Synchronous here: the issuing fiber (thread 0) runs before the others in every barrier phase, so the data is in place
+// when they pass the (no-op) mbarrier wait.  Like the hardware, refuse a start coordinate that is not 16-byte aligned
+// (the measured "illegal instruction").
+inline void tma_load_2d(void *dst, const CUtensorMap *m, int x, int y)
+{
+    if (((long long)x * m->elem) % 16 != 0) unsupported("TMA start coordinate not 16-byte aligned (faults on B200)");
+    tma_box_loads++;
+    for (int by = 0; by < m->bh; by++)
+        for (int bx = 0; bx < m->bw; bx++) {
+            char *d = (char *)dst + ((size_t)by * m->bw + bx) * m->elem;
+            const int sx = x + bx, sy = y + by;
+            if (sx >= 0 && sy >= 0 && sx < m->w && sy < m->h) memcpy(d, (const char *)m->base + (size_t)sy * m->pitch_bytes + (size_t)sx * m->elem, m->elem);
+            else memset(d, 0, m->elem);
+        }
+}
 }

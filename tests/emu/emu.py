@@ -27,6 +27,8 @@ def lib(defs: tuple[str, ...] = ()) -> C.CDLL:
         l.emu_destroy.argtypes = [C.c_void_p]
         l.emu_set_constants.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
         l.emu_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        l.emu_set_tma.argtypes = [C.c_void_p, C.c_int]
+        l.emu_tma_box_loads.restype = C.c_longlong
         l.emu_get_buffer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.emu_debug_view.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.emu_composite.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -46,8 +48,10 @@ def _aligned(a: np.ndarray) -> np.ndarray:
 class EmulatedFrame:
     """One frame through the host-compiled kernels, planned by a plan-only libmeao context (device = -1)."""
 
-    def __init__(self, plan, *, linear: bool = False, defs: tuple[str, ...] = ()):
-        """plan: miniengineao_b200.AmbientOcclusion(camera, device=-1) with parameters / variants already set."""
+    def __init__(self, plan, *, linear: bool = False, defs: tuple[str, ...] = (), use_tma: bool = True):
+        """plan: miniengineao_b200.AmbientOcclusion(camera, device=-1) with parameters / variants already set.
+        use_tma: interior tiles take the kernels' TMA path (emulated box loads) -- what runs on the GPU; False forces the
+        gather path everywhere (libmeao's MEAO_DISABLE_TMA=1)."""
         from miniengineao_b200 import _native as N
         self._lib = lib(defs)
         plan.LateUpdate()
@@ -67,6 +71,7 @@ class EmulatedFrame:
         else:       # Linearize(OOB load = 0): DS1:40-45
             pad12 = 1e5 if rz else float(np.float32(1) / np.float32(zb[1]))
         self._h = self._lib.emu_create(self.W, self.H)
+        self._lib.emu_set_tma(self._h, int(use_tma))
         self._lib.emu_set_constants(self._h, rc, rcw, uc, zb, pad12, int(not linear), int(rz), int(plan.highQualityMask), int(plan.sampleExhaustively))
 
     def __del__(self):
@@ -80,6 +85,10 @@ class EmulatedFrame:
         assert d.shape == (self.H, self.W)
         self._lib.emu_run(self._h, d.ctypes.data, fmt)
         return self.buffer(17)
+
+    def tma_box_loads(self) -> int:
+        """Emulated TMA box loads issued by this library instance so far (process-wide counter)."""
+        return int(self._lib.emu_tma_box_loads())
 
     def buffer(self, bid: int) -> np.ndarray:
         d = self.plan.buffer_desc(bid)

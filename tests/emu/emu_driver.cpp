@@ -28,7 +28,16 @@ struct Emu {
     float reject_fadeoff = -1, intensity = 1, pad[5] = {0, 0, 0, 0, 0};
     float nfs[5], step[5], kblur[5], tol[5];
     int hq_mask = 0, exhaustive = 0;
+    int use_tma = 1;        // 1: interior tiles take the kernels' TMA path (emulated box loads), 0: every tile gathers
 };
+
+// what MeaoCtx::make_map hands to cuTensorMapEncodeTiled
+CUtensorMap make_map(const void *base, int elem, int w, int h, int pitch_elems, int bw, int bh)
+{
+    CUtensorMap m{};
+    m.base = base; m.elem = elem; m.w = w; m.h = h; m.pitch_bytes = (size_t)pitch_elems * elem; m.bw = bw; m.bh = bh;
+    return m;
+}
 
 }  // namespace
 
@@ -101,8 +110,9 @@ static void run_render(Emu *e, int k, bool wide)
     for (int i = 0; i < n; i++) { a.inv_thickness[i] = it[idx[i]]; a.neg_front[i] = -(a.inv_thickness[i] - 0.5f); a.weight[i] = e->sample_weight[k][idx[i]]; }
     a.reject_fadeoff = e->reject_fadeoff; a.intensity = e->intensity;
     a.row0 = 0; a.row1 = e->lh[k]; a.wide = wide; a.exhaustive = e->exhaustive;
-    CUtensorMap dummy{};
-    launch_render_ao(dummy, false, a, nullptr);
+    const CUtensorMap map = wide ? make_map(e->low[k], 4, e->lw[k], e->lh[k], e->low_pitch[k], kRenderWideBoxW, kRenderWideBoxH)
+                                 : make_map(e->low[k], 4, e->lw[k], e->lh[k], e->low_pitch[k], kRenderBoxW, kRenderBoxH);
+    launch_render_ao(map, e->use_tma != 0, a, nullptr);
 }
 
 static void run_upsample(Emu *e, int lo)
@@ -124,9 +134,24 @@ static void run_upsample(Emu *e, int lo)
 #endif
     a.row0 = 0; a.row1 = e->lh[hi];
     const bool premin = ((e->hq_mask >> (lo - 1)) & 1) != 0;
-    CUtensorMap dummy{};
-    launch_blur_upsample(dummy, dummy, &dummy, false, a, premin ? e->hq[lo] : nullptr, e->occ_pitch[lo], nullptr);
+    const CUtensorMap md = make_map(e->low[lo], 4, e->lw[lo], e->lh[lo], e->low_pitch[lo], kUpsDepthBoxW, kUpsDepthBoxH);
+    const CUtensorMap ma = make_map(a.lo_ao, 1, e->lw[lo], e->lh[lo], e->occ_pitch[lo], kUpsAoBoxW, kUpsAoBoxH);
+    const CUtensorMap mh = make_map(e->hq[lo], 1, e->lw[lo], e->lh[lo], e->occ_pitch[lo], kUpsAoBoxW, kUpsAoBoxH);
+    launch_blur_upsample(md, ma, &mh, e->use_tma != 0, a, premin ? e->hq[lo] : nullptr, e->occ_pitch[lo], nullptr);
 }
+
+// aborts (on purpose) with the emulated TMA's alignment complaint: an f32 box starting at x = 3
+int emu_selfcheck_unaligned_tma()
+{
+    alignas(128) static float src[64 * 8], dst[16 * 4];
+    const CUtensorMap m = make_map(src, 4, 64, 8, 64, 16, 4);
+    meao_emu::tma_load_2d(dst, &m, 3, 0);
+    return 0;
+}
+
+long long emu_tma_box_loads() { return meao_emu::tma_box_loads; }
+
+void emu_set_tma(void *h, int use_tma) { ((Emu *)h)->use_tma = use_tma; }
 
 // in_format: 0 = f32, 1 = D16 codes, 2 = D24S8 words (PrepareArgs.in_format); depth must be 16-byte aligned
 void emu_run(void *h, const void *depth, int in_format)

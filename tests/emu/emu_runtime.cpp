@@ -10,6 +10,7 @@ uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
 
 namespace meao_emu {
+long long tma_box_loads = 0;
 namespace {
 constexpr size_t kStack = 256 * 1024;
 struct Fiber { ucontext_t ctx; bool done; char *stack; };

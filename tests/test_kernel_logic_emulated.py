@@ -4,6 +4,8 @@ one fiber per CUDA thread, fibers switch at __syncthreads) and run against the o
 What this proves: the kernels' logic -- tiling, aprons, border / padding handling, operation order, packed-lane bookkeeping,
 the variants' plumbing, every build switch -- is the reference's arithmetic.  What it cannot prove: anything about the real
 hardware path (TMA boxes, MUFU.RCP + refinement, memory model); that is what tests/test_parity_gpu.py does on the B200.
+TMA box loads are emulated as synchronous copies with zero fill, so interior tiles run the same TMA branch as on the GPU
+(use_tma=True, the default) and the gather branch can be forced everywhere (use_tma=False = MEAO_DISABLE_TMA=1).
 The emulator is test infrastructure: libmeao.so never contains it and still has no CPU path (test_abi.py).
 """
 import numpy as np
@@ -43,14 +45,16 @@ def _compare_all(f, orc, tag, mask=0):
     assert not bad, f"{tag}: mismatching buffers (id, #diff, size): {bad}"
 
 
-def _run(W, H, seed=1, defs=(), depth=None, **kw):
+def _run(W, H, seed=1, defs=(), depth=None, use_tma=True, **kw):
     okw = {k: v for k, v in kw.items()}
     orc = Oracle(W, H, threads=4, **okw)
     if depth is None:
         depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=seed), reversed_z=kw.get("reversed_z", True))
     ref = orc.run(depth)
-    f = EmulatedFrame(_plan(W, H, **kw), defs=tuple(defs))
+    f = EmulatedFrame(_plan(W, H, **kw), defs=tuple(defs), use_tma=use_tma)
+    n0 = f.tma_box_loads()
     got = f.run(depth)
+    f.tma_loads_in_run = f.tma_box_loads() - n0
     assert int((got != ref).sum()) == 0, (W, H, kw, defs)
     _compare_all(f, orc, f"{W}x{H} {kw} {defs}", kw.get("high_quality_mask", 0))
     return f, orc
@@ -89,8 +93,35 @@ def test_sky_pixels_take_the_ieee_fallbacks():
     _run(W, H, depth=depth, high_quality_mask=15, sample_exhaustively=True)
 
 
-def test_corridor_640x360():
-    _run(640, 360, depth=synth.lin01_to_raw(synth.corridor(640, 360)), intensity=1.1)
+@pytest.mark.parametrize("use_tma", [True, False])
+def test_corridor_640x360(use_tma):
+    """Large enough for interior tiles at levels 1-2 of the render and 0-1 of the upsample (the TMA branch)."""
+    f, _ = _run(640, 360, depth=synth.lin01_to_raw(synth.corridor(640, 360)), intensity=1.1, use_tma=use_tma)
+    # interior tiles: render L1 3 x 4 + L2 1 x 1, upsample L1->L0 8 x 9 (two boxes each) + L2->L1 3 x 3 ...
+    assert (f.tma_loads_in_run > 100) if use_tma else (f.tma_loads_in_run == 0), f.tma_loads_in_run
+
+
+@pytest.mark.parametrize("use_tma", [True, False])
+def test_variants_with_interior_tiles(use_tma):
+    """Wide render (80 x 48 box), premin upsample (second AO box) and exhaustive sampling on TMA-fed tiles; sky patch inside."""
+    W, H = 768, 400
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=13))
+    depth[150:230, 300:500] = 0.0
+    f, _ = _run(W, H, depth=depth, use_tma=use_tma, high_quality_mask=15, sample_exhaustively=True, intensity=1.2)
+    assert (f.tma_loads_in_run > 200) if use_tma else (f.tma_loads_in_run == 0), f.tma_loads_in_run
+
+
+def test_unaligned_tma_start_is_refused():
+    """on B200 a box whose start coordinate is not 16-byte aligned raises 'illegal instruction'; the emulated
+    TMA refuses the same thing, so a tile-origin change that breaks the rule fails here before it reaches the GPU."""
+    import ctypes as C
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, 'tests'); import ctypes as C; from emu.emu import lib; l = lib();"
+            "l.emu_selfcheck_unaligned_tma.restype = C.c_int; l.emu_selfcheck_unaligned_tma()")
+    import os
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode != 0 and "16-byte aligned" in r.stderr, (r.returncode, r.stderr[-300:])
 
 
 def test_linear_and_native_depth_ingest():
