@@ -13,10 +13,10 @@ KERNELS = ["prepare_depth.cu", "render_ao.cu", "blur_upsample.cu", "debug_view.c
 FLAGS = ["-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-DMEAO_EMULATE", "-I", HERE, "-Wno-unknown-pragmas", "-Wno-unused-function"]
 
 
-def is_stale() -> bool:
-    if not os.path.exists(LIB):
+def is_stale(lib: str = LIB) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".h", ".cpp", ".py"))]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -24,9 +24,7 @@ def is_stale() -> bool:
 def build(force: bool = False, defs: list[str] | None = None) -> str:
     """defs: extra -D switches (e.g. ["-DMEAO_UPS_STATIC_GUARD=1"]) -> a separately named library."""
     lib = LIB if not defs else os.path.join(HERE, "libmeao_emu_" + "_".join(d.replace("-D", "").replace("=", "") for d in defs) + ".so")
-    if not force and not defs and not is_stale():
-        return lib
-    if defs and os.path.exists(lib) and not force and os.path.getmtime(lib) > max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)):
+    if not force and not is_stale(lib):
         return lib
     objs = []
     tag = os.path.basename(lib)[:-3]
