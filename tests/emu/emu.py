@@ -29,6 +29,11 @@ def lib(defs: tuple[str, ...] = ()) -> C.CDLL:
         l.emu_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         l.emu_set_tma.argtypes = [C.c_void_p, C.c_int]
         l.emu_tma_box_loads.restype = C.c_longlong
+        l.emu_set_band.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        l.emu_poison_low.argtypes = [C.c_void_p]
+        l.emu_band_phase_a.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        l.emu_halo.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        l.emu_band_phase_b.argtypes = [C.c_void_p]
         l.emu_get_buffer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.emu_debug_view.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.emu_composite.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -85,6 +90,36 @@ class EmulatedFrame:
         assert d.shape == (self.H, self.W)
         self._lib.emu_run(self._h, d.ctypes.data, fmt)
         return self.buffer(17)
+
+    # ---- row bands: the plan must already carry the band (plan.set_row_band) -----------------------------------------
+    def use_plan_band(self) -> None:
+        rows = self.plan.band_rows()
+        prod = (C.c_int * 10)(*[v for lohi in rows["produce"] for v in lohi])
+        self.band = rows["produce"][0]
+        self._lib.emu_set_band(self._h, self.band[0], self.band[1], prod)
+        self._lib.emu_poison_low(self._h)
+
+    def band_phase_a(self, depth_band: np.ndarray) -> None:
+        d = _aligned(np.ascontiguousarray(depth_band, np.float32))
+        assert d.shape == (self.band[1] - self.band[0], self.W)
+        self._lib.emu_band_phase_a(self._h, d.ctypes.data, 0)
+
+    def halo_pack(self, side: int) -> np.ndarray:
+        rows = self.plan.halo_rows(side, True)
+        buf = _aligned(np.zeros(max(self.plan.halo_bytes(side) // 4, 1), np.float32))
+        self._lib.emu_halo(self._h, (C.c_int * 8)(*[v for lohi in rows for v in lohi]), buf.ctypes.data, 1)
+        return buf[:self.plan.halo_bytes(side) // 4]
+
+    def halo_unpack(self, side: int, packed: np.ndarray) -> None:
+        rows = self.plan.halo_rows(side, False)
+        buf = _aligned(np.ascontiguousarray(packed, np.float32)) if packed.size else _aligned(np.zeros(1, np.float32))
+        assert packed.size * 4 == self.plan.halo_recv_bytes(side)
+        self._lib.emu_halo(self._h, (C.c_int * 8)(*[v for lohi in rows for v in lohi]), buf.ctypes.data, 0)
+
+    def band_phase_b(self) -> np.ndarray:
+        """-> the band's rows of the AO texture"""
+        self._lib.emu_band_phase_b(self._h)
+        return self.buffer(17)[self.band[0]:self.band[1]]
 
     def tma_box_loads(self) -> int:
         """Emulated TMA box loads issued by this library instance so far (process-wide counter)."""

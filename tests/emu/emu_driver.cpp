@@ -29,6 +29,8 @@ struct Emu {
     float nfs[5], step[5], kblur[5], tol[5];
     int hq_mask = 0, exhaustive = 0;
     int use_tma = 1;        // 1: interior tiles take the kernels' TMA path (emulated box loads), 0: every tile gathers
+    // row band (meao_set_row_band): rows of level k to PRODUCE, k = 0..4 (meao_band_rows "produce"); default = whole frame
+    int band0 = 0, band1 = 0, need_lo[5] = {0, 0, 0, 0, 0}, need_hi[5] = {0, 0, 0, 0, 0};
 };
 
 // what MeaoCtx::make_map hands to cuTensorMapEncodeTiled
@@ -57,6 +59,8 @@ void *emu_create(int W, int H)
         e->hq[k] = alloc<uint8_t>((size_t)e->occ_pitch[k] * e->lh[k]);
         if (k <= 3) e->comb[k] = alloc<uint8_t>((size_t)e->occ_pitch[k] * e->lh[k]);
     }
+    e->band0 = 0; e->band1 = H;
+    for (int k = 0; k <= 4; k++) { e->need_lo[k] = 0; e->need_hi[k] = e->lh[k]; }
     return e;
 }
 
@@ -89,7 +93,7 @@ void emu_set_constants(void *h, const float *rc, const float *rcw, const float *
 static void run_downsample(Emu *e, const void *depth, int in_format)
 {
     PrepareArgs a{};
-    a.depth = depth; a.in_format = in_format; a.W = e->W; a.H = e->H; a.depth_row0 = 0; a.row0 = 0; a.row1 = e->H;
+    a.depth = depth; a.in_format = in_format; a.W = e->W; a.H = e->H; a.depth_row0 = e->band0; a.row0 = e->band0; a.row1 = e->band1;
     a.lin = e->lin; a.lin_pitch = e->lin_pitch;
     for (int k = 1; k <= 4; k++) { a.low[k - 1] = e->low[k]; a.low_pitch[k - 1] = e->low_pitch[k]; }
     a.zbx = e->zbx; a.zby = e->zby; a.raw = e->raw; a.reversed_z = e->reversed_z;
@@ -109,7 +113,7 @@ static void run_render(Emu *e, int k, bool wide)
     const float *it = wide ? e->inv_thickness_wide[k] : e->inv_thickness[k];
     for (int i = 0; i < n; i++) { a.inv_thickness[i] = it[idx[i]]; a.neg_front[i] = -(a.inv_thickness[i] - 0.5f); a.weight[i] = e->sample_weight[k][idx[i]]; }
     a.reject_fadeoff = e->reject_fadeoff; a.intensity = e->intensity;
-    a.row0 = 0; a.row1 = e->lh[k]; a.wide = wide; a.exhaustive = e->exhaustive;
+    a.row0 = e->need_lo[k]; a.row1 = e->need_hi[k]; a.wide = wide; a.exhaustive = e->exhaustive;
     const CUtensorMap map = wide ? make_map(e->low[k], 4, e->lw[k], e->lh[k], e->low_pitch[k], kRenderWideBoxW, kRenderWideBoxH)
                                  : make_map(e->low[k], 4, e->lw[k], e->lh[k], e->low_pitch[k], kRenderBoxW, kRenderBoxH);
     launch_render_ao(map, e->use_tma != 0, a, nullptr);
@@ -132,7 +136,7 @@ static void run_upsample(Emu *e, int lo)
     a.fast_div_ok = a.fast_div_ok && a.upsample_tolerance >= 2.7755575615628914e-17f && a.noise_filter_strength >= 2.220446049250313e-16f &&
                     a.noise_filter_strength < 576460752303423488.0f;
 #endif
-    a.row0 = 0; a.row1 = e->lh[hi];
+    a.row0 = e->need_lo[hi]; a.row1 = e->need_hi[hi];
     const bool premin = ((e->hq_mask >> (lo - 1)) & 1) != 0;
     const CUtensorMap md = make_map(e->low[lo], 4, e->lw[lo], e->lh[lo], e->low_pitch[lo], kUpsDepthBoxW, kUpsDepthBoxH);
     const CUtensorMap ma = make_map(a.lo_ao, 1, e->lw[lo], e->lh[lo], e->occ_pitch[lo], kUpsAoBoxW, kUpsAoBoxH);
@@ -158,6 +162,51 @@ void emu_run(void *h, const void *depth, int in_format)
 {
     Emu *e = (Emu *)h;
     run_downsample(e, depth, in_format);
+    for (int k = 1; k <= 4; k++) run_render(e, k, false);
+    for (int k = 1; k <= 4; k++) if ((e->hq_mask >> (k - 1)) & 1) run_render(e, k, true);
+    for (int lo = 4; lo >= 1; lo--) run_upsample(e, lo);
+}
+
+// ---- row bands: the two phases of meao_band_phase_a / _b around the neighbour exchange ----------------------------------
+// produce10 = meao_band_rows()[0..9]: rows of level k = 0..4 to produce; [row0, row1) = the band itself
+void emu_set_band(void *h, int row0, int row1, const int *produce10)
+{
+    Emu *e = (Emu *)h;
+    e->band0 = row0; e->band1 = row1;
+    for (int k = 0; k <= 4; k++) { e->need_lo[k] = produce10[2 * k]; e->need_hi[k] = produce10[2 * k + 1]; }
+}
+
+// every LowDepth texel becomes NaN: rows this band neither produces nor receives must never reach an output
+void emu_poison_low(void *h)
+{
+    Emu *e = (Emu *)h;
+    for (int k = 1; k <= 4; k++) for (size_t i = 0; i < (size_t)e->low_pitch[k] * e->lh[k]; i++) e->low[k][i] = __uint_as_float(0x7fc00000u);
+}
+
+// depth_band: the band's rows only (row1 - row0 rows), like meao_render_band_prepare
+void emu_band_phase_a(void *h, const void *depth_band, int in_format) { run_downsample((Emu *)h, depth_band, in_format); }
+
+// rows8 = meao_halo_rows(side, send): {lo1,hi1, ..., lo4,hi4}; packed message layout of meao_halo_pack (level 1 first, tight rows)
+void emu_halo(void *h, const int *rows8, float *packed, int pack)
+{
+    Emu *e = (Emu *)h;
+    HaloArgs a{}; a.nseg = 0;
+    float *p = packed;
+    for (int k = 1; k <= 4; k++) {
+        const int lo = rows8[2 * (k - 1)], rows = rows8[2 * (k - 1) + 1] - lo;
+        if (rows <= 0) continue;
+        float *buf = e->low[k] + (size_t)lo * e->low_pitch[k];
+        HaloSeg &g = a.seg[a.nseg++];
+        if (pack) g = HaloSeg{buf, p, e->low_pitch[k], e->lw[k], e->lw[k], rows};
+        else      g = HaloSeg{p, buf, e->lw[k], e->low_pitch[k], e->lw[k], rows};
+        p += (size_t)rows * e->lw[k];
+    }
+    launch_halo_copy(a, nullptr);
+}
+
+void emu_band_phase_b(void *h)
+{
+    Emu *e = (Emu *)h;
     for (int k = 1; k <= 4; k++) run_render(e, k, false);
     for (int k = 1; k <= 4; k++) if ((e->hq_mask >> (k - 1)) & 1) run_render(e, k, true);
     for (int lo = 4; lo >= 1; lo--) run_upsample(e, lo);

@@ -118,3 +118,56 @@ def test_partition_is_16_row_aligned_and_balanced():
         assert max(sizes) - min(sizes) <= 16 + (H % 16)
     assert rowtile.neighbours([0, 544, 1088], 0) == (-1, 1088)
     assert rowtile.neighbours([0, 544, 1088], 1) == (0, -1)
+
+
+def _worker_emulated(rank, world, port, W, H, q, mask):
+    """Same protocol as RowTiledAO.step, but with the HOST-COMPILED kernel sources (tests/emu) as the compute of each rank:
+    prepare_depth on the band -> halo_copy pack -> gloo exchange -> halo_copy unpack -> render / upsample on the band's rows."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from miniengineao_b200 import AmbientOcclusion, Camera, rowtile, synth
+    from oracle.oracle import Oracle
+    from emu.emu import EmulatedFrame
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=99))
+        ref = Oracle(W, H, intensity=1.1, high_quality_mask=mask).run(depth)
+        cuts = rowtile.partition(H, world)
+        r0, r1 = cuts[rank], cuts[rank + 1]
+        plan = AmbientOcclusion(Camera(W, H), device=-1)
+        plan.intensity, plan.highQualityMask = 1.1, mask
+        plan.set_row_band(r0, r1, *rowtile.neighbours(cuts, rank))
+        f = EmulatedFrame(plan)
+        f.use_plan_band()                                   # also poisons every LowDepth texel with NaN
+        f.band_phase_a(depth[r0:r1])                        # this rank only ever sees its band of the depth buffer
+        send = [torch.from_numpy(f.halo_pack(side).copy()) for side in (0, 1)]
+        recv = [torch.empty(plan.halo_recv_bytes(side) // 4, dtype=torch.float32) for side in (0, 1)]
+        rowtile.exchange(send[0], send[1], recv[0], recv[1], rank, world)
+        for side in (0, 1):
+            f.halo_unpack(side, recv[side].numpy())
+        got = f.band_phase_b()
+        q.put((rank, int((got != ref[r0:r1]).sum()), int(send[0].numel() + send[1].numel())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,W,H,mask", [(2, 192, 1088, 0), (3, 160, 1600, 0b1010)])
+def test_row_bands_with_emulated_kernels_over_gloo(world, W, H, mask):
+    """The multi-GPU band path end to end on CPU: the C planner's ranges, the REAL kernels' row-range logic (host build),
+    the halo pack / unpack kernel and the neighbour exchange; every LowDepth row a band neither owns nor receives is NaN."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_emulated, args=(r, world, port, W, H, q, mask)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    results = sorted(q.get(timeout=5) for _ in range(world))
+    assert all(r[1] == 0 for r in results), results
+    assert all(r[2] > 0 for r in results)
