@@ -245,6 +245,9 @@ int meao_composite_framebuffer(MeaoCtx *ctx, const void *ao_dev, void *color_dev
  * "Blend Zero OneMinusSrcColor, Zero OneMinusSrcAlpha" with src0 = (0,0,0,1-ao), src1 = (1-ao,1-ao,1-ao,0):
  *   gbuffer0.a *= 1-(1-ao)  (RGBA8, occlusion channel),  gbuffer3.rgb *= 1-(1-ao)  (ambient/emission target). */
 int meao_composite_gbuffer(MeaoCtx *ctx, const void *ao_dev, void *gbuffer0_rgba8_dev, void *gbuffer3_dev, int32_t gbuffer3_format, void *stream);
+/* replaces: PushCompositeCommands, debug branch (AO.cs:826-829) = Blit.shader pass 3 "Debug" (:116-134), no blending:
+ *   color.rgba = view.rrrr   where view_r8_dev is the width*height R8 image written by meao_debug_view (or the AO texture). */
+int meao_composite_debug(MeaoCtx *ctx, const void *view_r8_dev, void *color_dev, int32_t color_format, void *stream);
 
 /* ---- command-buffer hook (Unity native-plugin style) -------------------------------------------- */
 /* replaces: camera.AddCommandBuffer(..., _renderCommand) (AO.cs:412-429): a host engine issues

@@ -234,8 +234,15 @@ class AmbientOcclusion:
         return render, comp
 
     def composite(self, ao, *, color=None, gbuffer0=None, gbuffer3=None, stream=None) -> str:
-        """PushCompositeCommands (AO.cs:822-839): the ambient-only deferred branch multiplies the G-buffer occlusion and
-        ambient targets (Blit.shader pass 1), otherwise the frame buffer (pass 2).  Returns the branch taken."""
+        """PushCompositeCommands (AO.cs:822-839): with `debug` > 0 the selected debug view replaces the camera target
+        (Blit.shader pass 3); otherwise the ambient-only deferred branch multiplies the G-buffer occlusion and ambient
+        targets (pass 1), otherwise the frame buffer is multiplied (pass 2).  Returns the branch taken."""
+        if self._debug > 0:
+            if color is None:
+                raise ValueError("the debug composite needs the camera target")
+            view = ao if self._debug == 17 else self.debug_view(self._debug, stream=stream)       # AO.cs:815-819
+            self.composite_debug(view, color, stream=stream)
+            return "debug"
         if self.ambientOnlyEnabled:
             if gbuffer0 is None or gbuffer3 is None:
                 raise ValueError("ambient-only deferred composite needs gbuffer0 and gbuffer3 (AO.cs:595-598)")
@@ -259,6 +266,15 @@ class AmbientOcclusion:
         fmt = N.MEAO_FMT_RGBA16_FLOAT if gbuffer3.dtype == torch.float16 else N.MEAO_FMT_RGBA8_UNORM
         self._check(self._lib.meao_composite_gbuffer(self._ctx, ao.data_ptr(), gbuffer0.data_ptr(), gbuffer3.data_ptr(), fmt,
                                                      self._stream(stream)))
+
+    def composite_debug(self, view, color, *, stream=None) -> None:
+        """color (RGBA8 / RGBA16F, CUDA) = view.rrrr (Blit.shader pass 3, no blending)."""
+        import torch
+        fmt = N.MEAO_FMT_RGBA16_FLOAT if color.dtype == torch.float16 else N.MEAO_FMT_RGBA8_UNORM
+        self._check(self._lib.meao_composite_debug(self._ctx, view.data_ptr(), color.data_ptr(), fmt, self._stream(stream)))
+
+    # `debug` (AO.cs:60): 0 = normal composite, 1..17 = show that buffer instead
+    debug = property(lambda s: s._debug, lambda s, v: setattr(s, "_debug", int(v)))
 
     def synchronize(self) -> None:
         """Wait for the context's own stream (host-buffer path, debug copies) AND the current torch stream."""

@@ -44,7 +44,42 @@ __global__ void __launch_bounds__(256) debug_view_kernel(const DebugViewArgs a)
 #endif
 }
 
+// Blit.shader pass 3 "Debug" (:116-134), recorded by PushCompositeCommands when _debug > 0 (AO.cs:826-829):
+// cmd.Blit(_result, CameraTarget, material, 3) with no blending -- the target becomes (r, r, r, r), r = the R8 view.
+// 4 pixels per thread: one 32-bit load of codes, one 128-bit (RGBA8) or two 128-bit (RGBA16F) stores.
+template <bool HALF>
+__global__ void __launch_bounds__(256) debug_composite_kernel(const uint8_t *__restrict__ view, void *__restrict__ color, long long npix)
+{
+#ifdef MEAO_DEVICE_OK
+    const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= npix) return;
+    const int n = (npix - i4 >= 4) ? 4 : (int)(npix - i4);
+    uint32_t k[4] = {0, 0, 0, 0};
+    if (n == 4) { const uint32_t q = *reinterpret_cast<const uint32_t *>(view + i4); k[0] = q & 0xffu; k[1] = (q >> 8) & 0xffu; k[2] = (q >> 16) & 0xffu; k[3] = q >> 24; }
+    else for (int e = 0; e < n; e++) k[e] = view[i4 + e];
+    if (HALF) {
+        __half *dst = reinterpret_cast<__half *>(color) + i4 * 4;
+        for (int e = 0; e < n; e++) {
+            const __half h = __float2half_rn(unorm8_load(k[e]));          // R8 sample -> float -> RGBA16F store (RTNE)
+            dst[4 * e] = h; dst[4 * e + 1] = h; dst[4 * e + 2] = h; dst[4 * e + 3] = h;
+        }
+    } else {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(color) + i4;
+        for (int e = 0; e < n; e++) dst[e] = k[e] * 0x01010101u;          // store(load(k)) == k on every channel
+    }
+#endif
+}
+
 }  // namespace
+
+cudaError_t launch_debug_composite(const uint8_t *view, void *color, long long npix, int half, cudaStream_t s)
+{
+    const int blocks = (int)((npix + 4 * 256 - 1) / (4 * 256));
+    if (blocks <= 0) return cudaSuccess;
+    if (half) MEAO_LAUNCH((debug_composite_kernel<true>), blocks, 256, 0, s, view, color, npix);
+    else      MEAO_LAUNCH((debug_composite_kernel<false>), blocks, 256, 0, s, view, color, npix);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_debug_view(const DebugViewArgs &a, cudaStream_t s)
 {

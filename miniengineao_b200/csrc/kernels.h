@@ -125,6 +125,8 @@ struct DebugViewArgs {
     int W, H;
 };
 cudaError_t launch_debug_view(const DebugViewArgs &a, cudaStream_t s);
+// Blit.shader pass 3 (AO.cs:826-829): colour target (RGBA8 / RGBA16F, tight) = (r, r, r, r) of the R8 view
+cudaError_t launch_debug_composite(const uint8_t *view, void *color, long long npix, int half, cudaStream_t s);
 
 // ---- composite (Blit.shader passes 1 and 2): colour *= ao, 4 pixels per thread ------------------------
 cudaError_t launch_composite(const uint8_t *ao, void *color, long long npix, int half, int rgb, int alpha, int one_minus, cudaStream_t s);

@@ -1172,6 +1172,16 @@ int meao_composite_gbuffer(MeaoCtx *c, const void *ao, void *g0, void *g3, int32
     return MEAO_OK;
 }
 
+int meao_composite_debug(MeaoCtx *c, const void *view, void *color, int32_t fmt, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if ((rc = composite_args(c, view, color, fmt))) return rc;
+    const long long npix = (long long)c->W * (c->band1 - c->band0);
+    CUDA_TRY(c, launch_debug_composite((const uint8_t *)view, color, npix, fmt == MEAO_FMT_RGBA16_FLOAT, (cudaStream_t)stream));
+    c->launches++;
+    return MEAO_OK;
+}
+
 int meao_bind_event(MeaoCtx *c, int32_t event_id, const void *depth, int32_t kind, void *ao_out)
 {
     if (!c) return MEAO_ERR_INVALID;

@@ -764,3 +764,15 @@ void meao_oracle_composite_gbuffer(const uint8_t *ao_codes, uint8_t *gbuffer0_rg
         scale_px(gbuffer3_rgba, g3_is_half, i, f, 1, 0);
     }
 }
+
+/* pass 3: return tex2D(_AOTexture, uv).r to all four channels, no blend state (Blit.shader:116-134; AO.cs:826-829) */
+void meao_oracle_composite_debug(const uint8_t *view_codes, void *rgba, int is_half, size_t npix)
+{
+    for (size_t i = 0; i < npix; i++) {
+        float r = (float)view_codes[i] * (1.0f / 255.0f);
+        for (int ch = 0; ch < 4; ch++) {
+            if (is_half) ((uint16_t *)rgba)[i * 4 + ch] = meao_oracle_f32_to_f16_bits(r);
+            else ((uint8_t *)rgba)[i * 4 + ch] = meao_oracle_unorm8_code(r);
+        }
+    }
+}

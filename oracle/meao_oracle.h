@@ -125,6 +125,9 @@ void meao_oracle_run(MeaoOracle *o, const float *depth, int threads);          /
  *   tiled source:     Blit.shader pass 4 (:136-156): uv4 = uv*4, slice = floor(uv4.x) + 4*floor(uv4.y), point sample at frac(uv4);
  *   id 17: the AO result itself.  The R8 store applies the UNORM8 rule to the sampled value. */
 void meao_oracle_debug_view(const MeaoOracle *o, int debug_id, uint8_t *out_codes);
+/* Blit.shader pass 3 (:116-134) without blending, recorded at AO.cs:826-829: rgba = view.rrrr.  R8 -> RGBA8 keeps the code on
+ * every channel; R8 -> RGBA16F stores f16(code * (1/255)), RTNE. */
+void meao_oracle_composite_debug(const uint8_t *view_codes, void *rgba, int is_half, size_t npix);
 
 /* Composite passes.  Fixed-function output-merger blending restated in fp32:
  *   pass 2, Blit.shader:84-101 + "Blend Zero SrcAlpha"                          : dst.rgba *= ao

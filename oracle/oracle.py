@@ -84,6 +84,7 @@ def _lib(variant: str = "fma") -> C.CDLL:
         lib.meao_oracle_upsample_constants.argtypes = [C.POINTER(_OracleStruct), C.c_int, fp, fp, fp, fp, fp, fp]
         lib.meao_oracle_composite_framebuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
         lib.meao_oracle_composite_gbuffer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
+        lib.meao_oracle_composite_debug.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
         _libs[variant] = lib
     return _libs[variant]
 
@@ -256,3 +257,12 @@ def composite_gbuffer(ao_codes: np.ndarray, gbuffer0: np.ndarray, gbuffer3: np.n
     assert g0.dtype == np.uint8 and g3.dtype in (np.uint8, np.float16)
     _lib().meao_oracle_composite_gbuffer(ao.ctypes.data, g0.ctypes.data, g3.ctypes.data, int(g3.dtype == np.float16), ao.size)
     return g0, g3
+
+
+def composite_debug(view_codes: np.ndarray, like: np.ndarray) -> np.ndarray:
+    """Blit.shader pass 3: a new [..., 4] array of like's dtype (uint8 RGBA8 / float16 RGBA16F) = view.rrrr."""
+    v = np.ascontiguousarray(view_codes, np.uint8)
+    out = np.zeros(v.shape + (4,), like.dtype)
+    assert out.dtype in (np.uint8, np.float16)
+    _lib().meao_oracle_composite_debug(v.ctypes.data, out.ctypes.data, int(out.dtype == np.float16), v.size)
+    return out

@@ -37,6 +37,7 @@ def lib(defs: tuple[str, ...] = ()) -> C.CDLL:
         l.emu_get_buffer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.emu_debug_view.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.emu_composite.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]
+        l.emu_composite_debug.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]
         _libs[key] = l
     return _libs[key]
 
@@ -143,4 +144,11 @@ def composite(ao: np.ndarray, color: np.ndarray, *, rgb: bool, alpha: bool, one_
     out = _aligned(np.ascontiguousarray(color))
     a = _aligned(np.ascontiguousarray(ao, np.uint8))
     lib(defs).emu_composite(a.ctypes.data, out.ctypes.data, a.size, int(out.dtype == np.float16), int(rgb), int(alpha), int(one_minus))
+    return out.copy()
+
+
+def composite_debug(view: np.ndarray, like: np.ndarray, defs: tuple[str, ...] = ()) -> np.ndarray:
+    v = _aligned(np.ascontiguousarray(view, np.uint8))
+    out = _aligned(np.zeros(v.shape + (4,), like.dtype))
+    lib(defs).emu_composite_debug(v.ctypes.data, out.ctypes.data, v.size, int(out.dtype == np.float16))
     return out.copy()

@@ -259,4 +259,6 @@ void emu_composite(const uint8_t *ao, void *color, long long npix, int half, int
     launch_composite(ao, color, npix, half, rgb, alpha, one_minus, nullptr);
 }
 
+void emu_composite_debug(const uint8_t *view, void *color, long long npix, int half) { launch_debug_composite(view, color, npix, half, nullptr); }
+
 }  // extern "C"

@@ -15,7 +15,7 @@ from miniengineao_b200 import AmbientOcclusion, Camera, synth
 from oracle import oracle as O
 from oracle.oracle import Oracle
 
-from emu.emu import EmulatedFrame, composite  # noqa: E402  (tests/ is on sys.path via conftest)
+from emu.emu import EmulatedFrame, composite, composite_debug  # noqa: E402  (tests/ is on sys.path via conftest)
 
 
 def _plan(W, H, **kw):
@@ -162,6 +162,15 @@ def test_composite_passes():
         g0, g3 = O.composite_gbuffer(ao, c8, col)
         assert np.array_equal(composite(ao, c8, rgb=False, alpha=True, one_minus=True), g0)
         assert np.array_equal(composite(ao, col, rgb=True, alpha=False, one_minus=True).view(np.uint8), g3.view(np.uint8))
+
+
+def test_debug_composite_pass3():
+    """Blit.shader pass 3 (AO.cs:826-829): target = view.rrrr, on sizes that are and are not multiples of the 4-pixel step."""
+    rng = np.random.default_rng(1)
+    for shape in ((45, 67), (1, 1), (3, 5), (64, 64)):
+        v = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        for like in (np.zeros(1, np.uint8), np.zeros(1, np.float16)):
+            assert np.array_equal(composite_debug(v, like).view(np.uint8), O.composite_debug(v, like).view(np.uint8)), (shape, like.dtype)
 
 
 @pytest.mark.parametrize("defs", [

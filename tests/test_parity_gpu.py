@@ -739,3 +739,26 @@ def test_cuda_reproduces_golden_fixture(torch_cuda, path):
         assert buf.dtype == ref.dtype and buf.shape == ref.shape, (bid, buf.dtype, buf.shape, ref.dtype, ref.shape)
         view = {1: np.uint8, 2: np.uint16, 4: np.uint32}[ref.dtype.itemsize]
         assert np.array_equal(buf.view(view), ref.view(view)), (os.path.basename(path), bid)
+
+
+def test_debug_composite_replaces_the_camera_target(torch_cuda):
+    """PushCompositeCommands with `debug` > 0 (AO.cs:826-829): the selected debug view lands on the camera target through
+    Blit.shader pass 3 (rgba = view.rrrr, no blending); debug == 17 shows the AO texture itself."""
+    from miniengineao_b200 import synth
+    from oracle import oracle as O
+    torch = torch_cuda
+    W, H = 322, 190
+    ao, orc = _mk(W, H, intensity=1.1)
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=6))
+    ref_ao = orc.run(depth)
+    ao_dev = ao.render(torch.from_numpy(depth).cuda())
+    for dbg in (6, 10, 17):
+        ao.debug = dbg
+        view = ref_ao if dbg == 17 else orc.debug_view(dbg)
+        for like in (np.zeros((H, W, 4), np.uint8), np.zeros((H, W, 4), np.float16)):
+            target = torch.from_numpy(like.copy()).cuda()
+            assert ao.composite(ao_dev, color=target) == "debug"
+            torch.cuda.synchronize()
+            assert np.array_equal(target.cpu().numpy().view(np.uint8), O.composite_debug(view, like).view(np.uint8)), (dbg, like.dtype)
+    ao.debug = 0
+    assert np.array_equal(ao.render(torch.from_numpy(depth).cuda()).cpu().numpy(), ref_ao)       # the debug property re-plans, nothing else
