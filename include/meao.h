@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define MEAO_ABI_VERSION 2   /* 2: + MeaoVariants, meao_stage_render_wide, meao_debug_view, buffer ids 18..21 */
+#define MEAO_ABI_VERSION 2   /* 2: + MeaoVariants, meao_stage_render_wide, meao_debug_view, meao_composite_debug, buffer ids 18..21 */
 
 typedef struct MeaoCtx MeaoCtx;
 
