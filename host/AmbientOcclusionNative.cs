@@ -43,7 +43,7 @@ namespace MiniEngineAO
 
         // Variants the reference ships in its shaders but never selects (meao.h: MeaoVariants); all zero = reference behaviour.
         [StructLayout(LayoutKind.Sequential)]
-        public struct MeaoVariants { public int single_pass_stereo, sample_exhaustively, high_quality_mask; }
+        public struct MeaoVariants { public int single_pass_stereo, sample_exhaustively, high_quality_mask, single_scale; }
 
         [DllImport(Lib)] public static extern int meao_create(ref MeaoDeviceCfg cfg, out IntPtr ctx);
         [DllImport(Lib)] public static extern void meao_destroy(IntPtr ctx);
@@ -54,7 +54,7 @@ namespace MiniEngineAO
         [DllImport(Lib)] public static extern int meao_resize(IntPtr ctx, int width, int height);
         [DllImport(Lib)] public static extern int meao_render(IntPtr ctx, IntPtr depthDev, int depthKind, IntPtr aoOutDev, IntPtr stream);
         [DllImport(Lib)] public static extern int meao_render_host(IntPtr ctx, float[] depth, int depthKind, byte[] aoOut);
-        [DllImport(Lib)] public static extern int meao_bind_event(IntPtr ctx, int eventId, IntPtr depthDev, int depthKind, IntPtr aoOutDev);
+        [DllImport(Lib)] public static extern int meao_bind_event(IntPtr ctx, int eventId, IntPtr depthDev, int depthKind, IntPtr aoOutDev, IntPtr stream);
         [DllImport(Lib)] public static extern IntPtr meao_get_render_event_func();
         [DllImport(Lib)] public static extern int meao_composite_framebuffer(IntPtr ctx, IntPtr aoDev, IntPtr colorDev, int colorFormat, IntPtr stream);
         [DllImport(Lib)] public static extern int meao_composite_gbuffer(IntPtr ctx, IntPtr aoDev, IntPtr gbuffer0Dev, IntPtr gbuffer3Dev, int gbuffer3Format, IntPtr stream);
@@ -109,6 +109,7 @@ namespace MiniEngineAO
         IntPtr _ctx = IntPtr.Zero;
         CommandBuffer _renderCommand;
         IntPtr _depthDev = IntPtr.Zero, _aoDev = IntPtr.Zero;   // mapped by the engine-specific interop layer
+        IntPtr _stream = IntPtr.Zero;                           // cudaStream_t the plugin event renders on (ABI 3; Zero = legacy default stream)
 
         void LateUpdate()
         {
@@ -144,7 +145,8 @@ namespace MiniEngineAO
             var variants = new MeaoNative.MeaoVariants
             {
                 single_pass_stereo = stereo ? 1 : 0,                                         // :680
-                sample_exhaustively = _sampleExhaustively ? 1 : 0, high_quality_mask = _highQualityMask
+                sample_exhaustively = _sampleExhaustively ? 1 : 0, high_quality_mask = _highQualityMask,
+                single_scale = 0                                                             // BASELINE configs[0] plumbing mode; the component never selects it
             };
             rebuild |= MeaoNative.meao_set_variants(_ctx, ref variants) == 1;
             rebuild |= MeaoNative.meao_resize(_ctx, _camera.pixelWidth * (stereo ? 2 : 1), _camera.pixelHeight) == 1;   // :338-341
@@ -160,7 +162,7 @@ namespace MiniEngineAO
             else _camera.RemoveCommandBuffer(CameraEvent.BeforeImageEffects, _renderCommand);
             _renderCommand.Clear();
             // (engine-specific: map _CameraDepthTexture and the R8 AO render texture to _depthDev / _aoDev)
-            MeaoNative.Check(_ctx, MeaoNative.meao_bind_event(_ctx, kEventId, _depthDev, 0 /* MEAO_DEPTH_RAW_F32 */, _aoDev));
+            MeaoNative.Check(_ctx, MeaoNative.meao_bind_event(_ctx, kEventId, _depthDev, 0 /* MEAO_DEPTH_RAW_F32 */, _aoDev, _stream));
             // one plugin event replaces the ten DispatchCompute calls recorded by :511-531
             _renderCommand.IssuePluginEvent(MeaoNative.meao_get_render_event_func(), kEventId);
             _camera.AddCommandBuffer(CameraEvent.BeforeImageEffects, _renderCommand);          // :421

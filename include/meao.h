@@ -30,7 +30,9 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define MEAO_ABI_VERSION 2   /* 2: + MeaoVariants, meao_stage_render_wide, meao_debug_view, meao_composite_debug, buffer ids 18..21 */
+#define MEAO_ABI_VERSION 3   /* 2: + MeaoVariants, meao_stage_render_wide, meao_debug_view, meao_composite_debug, buffer ids 18..21
+                              * 3: + MeaoVariants.single_scale, native peer halo exchange (meao_band_export / _connect / _step / _status),
+                              *      meao_bind_event takes the stream */
 
 typedef struct MeaoCtx MeaoCtx;
 
@@ -39,7 +41,8 @@ typedef enum {
     MEAO_ERR_INVALID = -1,      /* bad argument / call order */
     MEAO_ERR_CUDA = -2,         /* CUDA runtime or driver error, or no usable device */
     MEAO_ERR_UNSUPPORTED = -3,  /* e.g. halo deeper than the neighbouring band */
-    MEAO_ERR_NOMEM = -4
+    MEAO_ERR_NOMEM = -4,
+    MEAO_ERR_PEER = -5          /* native halo exchange: a neighbour did not arrive within the time-out (meao_band_status) */
 } MeaoStatus;
 
 /* AmbientOcclusion.cs:20-68 -- the serialized parameter surface, same names, ranges, defaults. */
@@ -112,6 +115,9 @@ typedef struct {
                                      HighQuality<k>, and the upsample whose LOW level is k runs Upsample.compute kernel "main_premin" /
                                      "main_premin_blendout" (:23,25,32-34,58-60) with LoResAO2 = HighQuality<k>.  E.g. 8 = coarsest level
                                      only, 15 = every level (the quality ladder of the upstream MiniEngine sample, which is not vendored). */
+    int32_t single_scale;         /* BASELINE.json configs[0] "single-scale AO": the frame is Downsample1 -> Render level 1 -> the FINAL-style
+                                     Upsample (kernel "main", AO.cs:531's dispatch with LoResAO1 = Occlusion1 instead of Combined1): three of
+                                     the ten dispatches of AO.cs:511-531, no coarser level contributes.  Requires high_quality_mask == 0. */
 } MeaoVariants;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -134,7 +140,9 @@ int meao_get_variants(const MeaoCtx *ctx, MeaoVariants *out);
 /* replaces: CalculateZBufferParams / CalculateTanHalfFovHeight inputs (AO.cs:561-573). */
 int meao_set_camera(MeaoCtx *ctx, const MeaoCamera *camera);
 /* replaces: RTHandle.SetBaseDimensions + AllocateNow + the rebuild it triggers (AO.cs:338-341, 501-506).
- * Allocates the intermediates for width x height.  Returns 1 if dimensions changed, 0 if not. */
+ * Allocates the intermediates for width x height.  Returns 1 if dimensions changed, 0 if not.
+ * A size change RESETS the row band to the whole frame and drops the neighbour connections (meao_set_row_band,
+ * meao_band_connect): a band host must set its band again after every call that returned 1. */
 int meao_resize(MeaoCtx *ctx, int32_t width, int32_t height);
 
 /* ---- the frame ------------------------------------------------------------------------------- */
@@ -232,6 +240,33 @@ int meao_render_band_finish(MeaoCtx *ctx, void *ao_band_out_dev, void *stream);
 int meao_band_phase_a(MeaoCtx *ctx, const void *depth_band_dev, int32_t depth_kind, void *send_up_dev, void *send_down_dev, void *stream);
 int meao_band_phase_b(MeaoCtx *ctx, const void *recv_up_dev, const void *recv_down_dev, void *ao_band_out_dev, void *stream);
 
+/* ---- native neighbour exchange (ABI 3): the halo rows travel by PEER STORES over NVLink, inside the frame's one CUDA graph ----
+ * Every band context keeps its LowDepth1..4 in full-frame global coordinates, so a band's border rows have the SAME byte offset
+ * in every context's arena: the exchange kernel (csrc/band_exchange.cu) writes them straight into the neighbour's LowDepth
+ * buffers through a peer mapping -- no pack, no staging, no unpack, no NCCL call -- then raises an epoch flag in the neighbour's
+ * memory (st.release.sys) and waits for the neighbour's own flag (ld.acquire.sys).  A step of a connected band is ONE graph
+ * launch: prepare_depth -> exchange -> Render x4 + Upsample x4 (DAG), no host code between the phases.
+ *   1. meao_resize + meao_set_row_band on every band context (one per GPU; same or different processes)
+ *   2. meao_band_export -> an opaque POD handle; move it to the neighbours any way the host likes (memcpy in-process;
+ *      torch.distributed / MPI / a pipe between processes -- it contains a cudaIpcMemHandle_t)
+ *   3. meao_band_connect(ctx, side, &neighbour_handle) for each existing neighbour (side 0 = up, 1 = down)
+ *   4. per frame, on every band in lock step: meao_band_step (asynchronous on `stream`)
+ * All bands must run the same number of steps.  A wait that exceeds the time-out (default 2 s, env MEAO_BAND_TIMEOUT_MS)
+ * sets a sticky error instead of hanging the GPU: the remaining kernels of that step still run (on stale halo rows),
+ * meao_band_status reports it and the next meao_band_step fails with MEAO_ERR_PEER.
+ * meao_resize and meao_set_row_band DISCONNECT (the arena / the halo ranges change): export + connect again afterwards. */
+#define MEAO_PEER_HANDLE_BYTES 128
+typedef struct { unsigned char bytes[MEAO_PEER_HANDLE_BYTES]; } MeaoPeerHandle;
+int meao_band_export(MeaoCtx *ctx, MeaoPeerHandle *out);
+/* peer == NULL disconnects that side.  Same process: direct pointer (+ cudaDeviceEnablePeerAccess across devices);
+ * another process: cudaIpcOpenMemHandle.  Fails with MEAO_ERR_INVALID if the neighbour's frame size differs. */
+int meao_band_connect(MeaoCtx *ctx, int32_t side, const MeaoPeerHandle *peer);
+int meao_band_step(MeaoCtx *ctx, const void *depth_band_dev, int32_t depth_kind, void *ao_band_out_dev, void *stream);
+/* out4 = { epoch of the next exchange (1 + completed exchanges), sticky error (0 ok, 1 = time-out waiting for a neighbour's
+ * ack, 2 = time-out waiting for a neighbour's rows), connected-up, connected-down }.  Synchronises nothing: reads the
+ * flags with a stream-less copy, so call it after the stream has drained for a definitive answer. */
+int meao_band_status(MeaoCtx *ctx, int32_t out4[4]);
+
 /* ---- composite: the consumer end of the pipe ------------------------------------------- */
 typedef enum {
     MEAO_FMT_RGBA8_UNORM = 0,   /* ARGB32-class LDR target, 4 bytes / pixel */
@@ -253,13 +288,18 @@ int meao_composite_debug(MeaoCtx *ctx, const void *view_r8_dev, void *color_dev,
 /* replaces: camera.AddCommandBuffer(..., _renderCommand) (AO.cs:412-429): a host engine issues
  * CommandBuffer.IssuePluginEvent(meao_get_render_event_func(), event_id). */
 typedef void (*MeaoRenderEventFunc)(int event_id);
-int meao_bind_event(MeaoCtx *ctx, int32_t event_id, const void *depth_dev, int32_t depth_kind, void *ao_out_dev);
+/* stream: the cudaStream_t the plugin event renders on (ABI 3; NULL = the CUDA legacy default stream, as before). */
+int meao_bind_event(MeaoCtx *ctx, int32_t event_id, const void *depth_dev, int32_t depth_kind, void *ao_out_dev, void *stream);
 void meao_render_event(int event_id);
 MeaoRenderEventFunc meao_get_render_event_func(void);
 
 /* ---- introspection ------------------------------------------------------------------------------ */
 int64_t meao_launch_count(const MeaoCtx *ctx);       /* kernels launched (or replayed via graph) so far */
-int meao_kernels_per_frame(const MeaoCtx *ctx);      /* kernel nodes in one frame: 9 + one per bit of high_quality_mask */
+/* Programmatic-dependent-launch level of the captured frame graphs: -1 = nothing captured yet, 0 = plain edges, 1 = PDL on the
+ * kernels whose only predecessor is the kernel before them in their stream, 2 = also where a cross-branch event joins.  The runtime
+ * decides what it accepts at the first capture; env MEAO_PDL=0|1|2 caps it. */
+int meao_pdl_level(const MeaoCtx *ctx);
+int meao_kernels_per_frame(const MeaoCtx *ctx);      /* kernel nodes in one frame: 9 + one per bit of high_quality_mask (3 with single_scale) */
 /* Algorithmic bytes of the reference data-flow: stage 0 = whole frame, 1 = Downsample1,
  * 2 = Downsample2, 3 = Render x4, 4 = Upsample x4, 5 = final Upsample (L1->L0) only. */
 int64_t meao_algorithmic_bytes(const MeaoCtx *ctx, int32_t stage);

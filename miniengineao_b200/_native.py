@@ -8,7 +8,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmeao.so")
 
-MEAO_OK, MEAO_ERR_INVALID, MEAO_ERR_CUDA, MEAO_ERR_UNSUPPORTED, MEAO_ERR_NOMEM = 0, -1, -2, -3, -4
+MEAO_OK, MEAO_ERR_INVALID, MEAO_ERR_CUDA, MEAO_ERR_UNSUPPORTED, MEAO_ERR_NOMEM, MEAO_ERR_PEER = 0, -1, -2, -3, -4, -5
+MEAO_ABI_VERSION = 3
+MEAO_PEER_HANDLE_BYTES = 128
 MEAO_FLAG_NONE, MEAO_FLAG_NO_GRAPH = 0, 1
 MEAO_DEPTH_RAW_F32, MEAO_DEPTH_LINEAR_F32, MEAO_DEPTH_RAW_D16_UNORM, MEAO_DEPTH_RAW_D24S8 = 0, 1, 2, 3
 MEAO_FMT_RGBA8_UNORM, MEAO_FMT_RGBA16_FLOAT = 0, 1
@@ -30,7 +32,12 @@ class MeaoDeviceCfg(C.Structure):
 
 
 class MeaoVariants(C.Structure):
-    _fields_ = [("single_pass_stereo", C.c_int32), ("sample_exhaustively", C.c_int32), ("high_quality_mask", C.c_int32)]
+    _fields_ = [("single_pass_stereo", C.c_int32), ("sample_exhaustively", C.c_int32), ("high_quality_mask", C.c_int32),
+                ("single_scale", C.c_int32)]
+
+
+class MeaoPeerHandle(C.Structure):
+    _fields_ = [("bytes", C.c_ubyte * MEAO_PEER_HANDLE_BYTES)]
 
 
 class MeaoBufferDesc(C.Structure):
@@ -85,10 +92,15 @@ SIGNATURES = {
     "meao_composite_framebuffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "meao_composite_gbuffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "meao_composite_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
-    "meao_bind_event": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "meao_band_export": (C.c_int, [C.c_void_p, C.POINTER(MeaoPeerHandle)]),
+    "meao_band_connect": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(MeaoPeerHandle)]),
+    "meao_band_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "meao_band_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "meao_bind_event": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "meao_render_event": (None, [C.c_int]),
     "meao_get_render_event_func": (RENDER_EVENT_FUNC, []),
     "meao_launch_count": (C.c_int64, [C.c_void_p]),
+    "meao_pdl_level": (C.c_int, [C.c_void_p]),
     "meao_kernels_per_frame": (C.c_int, [C.c_void_p]),
     "meao_algorithmic_bytes": (C.c_int64, [C.c_void_p, C.c_int32]),
     "meao_selftest_div": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),

@@ -79,6 +79,8 @@ class AmbientOcclusion:
         # shader variants the reference ships but never selects; defaults = reference behaviour
         self.sampleExhaustively = False     # Render.compute:144-159
         self.highQualityMask = 0            # bit k-1: Render.compute kernel "main" on level k + Upsample main_premin*
+        self.singleScale = False            # BASELINE.json configs[0]: Downsample1 -> Render level 1 -> final-style Upsample only
+        self._band = None                   # (row0, row1) after set_row_band; reset by every re-allocation
         self._drawCountPerFrame = 0         # AO.cs:289: used to detect single-pass stereo
         self._stereo = False                # singlePassStereoEnabled as latched by the last LateUpdate
         self.rebuild_count = 0
@@ -139,11 +141,13 @@ class AmbientOcclusion:
         if frame:
             self._stereo = self.singlePassStereoEnabled       # evaluated once per frame, before the counter reset (AO.cs:338-349)
         stereo = self._stereo
-        v = N.MeaoVariants(int(stereo), int(self.sampleExhaustively), int(self.highQualityMask))
+        v = N.MeaoVariants(int(stereo), int(self.sampleExhaustively), int(self.highQualityMask), int(self.singleScale))
         rebuild |= self._check(self._lib.meao_set_variants(self._ctx, C.byref(v))) == 1
         width = cam.pixelWidth * (2 if stereo else 1)                                                # AO.cs:338-341, 501-504
         resized = self._check(self._lib.meao_resize(self._ctx, width, cam.pixelHeight)) == 1          # CheckBaseDimensions
         self._width, self._height = width, cam.pixelHeight
+        if resized:
+            self._band = None       # meao_resize re-allocates: the C context is back to the whole frame and has dropped its neighbours
         if rebuild or resized:
             self.rebuild_count += 1
         if frame:
@@ -380,8 +384,7 @@ class AmbientOcclusion:
         self._band = (row0, row1)
 
     def _band_rows(self) -> int:
-        b = getattr(self, "_band", None)
-        return self._height if b is None else b[1] - b[0]
+        return self._height if self._band is None else self._band[1] - self._band[0]
 
     def band_rows(self) -> dict:
         """Row ranges of this band per level: rows to produce, LowDepth rows read, LowDepth rows owned."""
@@ -418,6 +421,32 @@ class AmbientOcclusion:
     def band_finish(self, out_band, stream=None) -> None:
         self._check(self._lib.meao_render_band_finish(self._ctx, out_band.data_ptr(), self._stream(stream)))
 
+    # native neighbour exchange (ABI 3): peer stores over NVLink inside the frame's graph, no host code between the phases
+    def band_export(self) -> bytes:
+        """Opaque handle of this band's arena (contains a cudaIpcMemHandle_t); hand it to the neighbours."""
+        h = N.MeaoPeerHandle()
+        self._check(self._lib.meao_band_export(self._ctx, C.byref(h)))
+        return bytes(h.bytes)
+
+    def band_connect(self, side: int, handle: bytes | None) -> None:
+        """side 0 = the band above, 1 = below; None disconnects."""
+        if handle is None:
+            self._check(self._lib.meao_band_connect(self._ctx, side, None))
+            return
+        h = N.MeaoPeerHandle()
+        C.memmove(h.bytes, handle, N.MEAO_PEER_HANDLE_BYTES)
+        self._check(self._lib.meao_band_connect(self._ctx, side, C.byref(h)))
+
+    def band_step(self, depth_band, out_band, *, linear: bool = False, stream=None) -> None:
+        """One frame of a connected band as ONE CUDA graph: prepare_depth -> peer exchange -> render x4 + upsample x4."""
+        kind = self._kind(str(depth_band.dtype).replace("torch.", ""), linear)
+        self._check(self._lib.meao_band_step(self._ctx, depth_band.data_ptr(), kind, out_band.data_ptr(), self._stream(stream)))
+
+    def band_status(self) -> dict:
+        out = (C.c_int32 * 4)()
+        self._check(self._lib.meao_band_status(self._ctx, out))
+        return {"epoch": out[0], "error": out[1], "connected": (bool(out[2]), bool(out[3]))}
+
     def band_phase_a(self, depth_band, send_up, send_down, *, linear: bool = False, stream=None) -> None:
         """prepare_depth on the band + pack of both halos, replayed as one CUDA graph."""
         kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
@@ -433,6 +462,11 @@ class AmbientOcclusion:
     @property
     def launch_count(self) -> int:
         return self._lib.meao_launch_count(self._ctx)
+
+    @property
+    def pdl_level(self) -> int:
+        """Programmatic-dependent-launch level the captured graphs use (-1 before the first capture)."""
+        return self._lib.meao_pdl_level(self._ctx)
 
     @property
     def kernels_per_frame(self) -> int:

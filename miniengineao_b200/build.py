@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmeao.so")
-SOURCES = ["meao_api.cu", "prepare_depth.cu", "render_ao.cu", "blur_upsample.cu", "selftest.cu", "halo.cu", "composite.cu", "debug_view.cu"]
+SOURCES = ["meao_api.cu", "prepare_depth.cu", "render_ao.cu", "blur_upsample.cu", "selftest.cu", "halo.cu", "band_exchange.cu", "composite.cu", "debug_view.cu"]
 HEADERS = ["common.cuh", "kernels.h", "blur_upsample_kernel.inc", os.path.join("..", "..", "include", "meao.h")]
 
 NVCC_FLAGS = [
@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
     "-Xptxas", "-v",
-    "-shared", "-cudart", "static",
+    "-shared", "-cudart", "static", "--threads", "0",
     "-Xlinker", "--exclude-libs,ALL", "-Xlinker", "-Bsymbolic",
 ]
 

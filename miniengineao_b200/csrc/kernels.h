@@ -25,12 +25,29 @@
 #include <stdint.h>
 
 // Kernel launch.  `k` is the kernel name IN PARENTHESES (they protect the commas of template arguments from the
-// preprocessor); in the CUDA build the macro expands to exactly  kernel<...><<<grid, block, smem, stream>>>(args).
+// preprocessor).  CUDA build: cudaLaunchKernelEx, with the programmatic-dependent-launch attribute when the recorder asked
+// for it (meao::g_launch_pdl, set by meao_api.cu around the launches whose predecessor IN THE SAME STREAM is one of our
+// kernels): the dependent grid may then be scheduled while its predecessor drains, runs its prologue and blocks in
+// pdl_wait() (griddepcontrol.wait) until the predecessor has completed and flushed -- see common.cuh.
 #define MEAO_UNPAREN(...) __VA_ARGS__
 #ifdef MEAO_EMULATE
 #define MEAO_LAUNCH(k, grid, block, smem, stream, ...) meao_emu::launch((grid), (block), (smem), [&]() { MEAO_UNPAREN k(__VA_ARGS__); })
 #else
-#define MEAO_LAUNCH(k, grid, block, smem, stream, ...) MEAO_UNPAREN k<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+namespace meao {
+inline thread_local bool g_launch_pdl = false;
+template <class... KArgs, class... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_launch_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+}  // namespace meao
+#define MEAO_LAUNCH(k, grid, block, smem, stream, ...) (void)meao::launch_ex(MEAO_UNPAREN k, (grid), (block), (smem), (stream), __VA_ARGS__)
 #endif
 
 namespace meao {
@@ -70,13 +87,14 @@ struct RenderArgs {
     int wide;               // 0: kernel main_interleaved (virtual f16 atlas of level k+2); 1: kernel main (WIDE_SAMPLING on f32 LowDepth<k>;
                             //    sw/sh/pad unused, low_map must carry the kRenderWideBox box)
     int exhaustive;         // SAMPLE_EXHAUSTIVELY (Render.compute:144-159)
+    int tile_h;             // output rows per CTA, one of kRenderTileHs (32: big levels; 16 / 8: coarse levels -- 2x / 4x the CTAs and a half / a
+                            //    quarter of the per-CTA latency: the coarse renders are latency-bound); low_map must carry the matching box
 };
 cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const RenderArgs &a, cudaStream_t s);
-#ifndef MEAO_REN_TH
-#define MEAO_REN_TH 32
-#endif
-constexpr int kRenderBoxW = 96, kRenderBoxH = MEAO_REN_TH + 32;     // TMA box of the render kernel (f32 elements)
-constexpr int kRenderWideBoxW = 80, kRenderWideBoxH = MEAO_REN_TH + 16;   // ... of its WIDE_SAMPLING variant (apron 8)
+constexpr int kRenderTileVariants = 3;
+constexpr int kRenderTileHs[kRenderTileVariants] = {32, 16, 8};
+constexpr int kRenderBoxW = 96, kRenderWideBoxW = 80;               // TMA box widths of the render kernel (f32 elements): 64 + 2 x apron (16 / wide: 8)
+constexpr int render_box_h(int tile_h, bool wide) { return tile_h + (wide ? 16 : 32); }
 
 // ---- stage 3: blur_upsample = Upsample.compute main / main_blendout, one level ----------------
 struct UpsampleArgs {
@@ -133,6 +151,28 @@ cudaError_t launch_composite(const uint8_t *ao, void *color, long long npix, int
 
 // ---- self test: div_fast / rcp_fast vs the IEEE operators on n random in-range operand pairs ------
 cudaError_t launch_selftest_div(uint64_t n, uint32_t seed, unsigned long long *mismatch_dev, cudaStream_t s);
+
+// ---- native neighbour exchange (include/meao.h "native neighbour exchange"): peer stores + epoch flags, one launch ------
+// Flags live in every band context's arena (zeroed at allocation).  ready / ack are written by the NEIGHBOURS through
+// their peer mapping; epoch / done / error are local.
+struct BandFlags {
+    uint32_t ready[2];      // [side]: epoch of the halo rows the neighbour on `side` has delivered into this arena
+    uint32_t ack[2];        // [side]: epoch the neighbour on `side` is about to RECEIVE, i.e. everything it read before is consumed
+    uint32_t epoch;         // epoch of this context's next exchange (first = 1)
+    uint32_t done;          // CTA completion counter of the running exchange kernel
+    uint32_t error;         // sticky: 0 ok, 1 timed out waiting for an ack, 2 timed out waiting for rows
+    uint32_t pad_;
+};
+struct XchgSeg { const uint4 *src; uint4 *dst; uint32_t n16; int32_t side; };     // one flat 16-byte-granular copy into the neighbour on `side`
+struct XchgArgs {
+    XchgSeg seg[8];         // LowDepth1..4 border rows x 2 sides (whole pitched rows: contiguous, 128-byte aligned)
+    int nseg;
+    BandFlags *local;
+    BandFlags *peer[2];     // neighbour's flags through the peer mapping; nullptr = no neighbour on that side
+    uint32_t *host_error;   // mapped host word mirroring local->error (may be nullptr)
+    unsigned long long timeout_ns;
+};
+cudaError_t launch_band_exchange(const XchgArgs &a, cudaStream_t s);
 
 // ---- halo pack / unpack: row blocks of pitched buffers <-> contiguous staging, one launch ------
 struct HaloSeg { const float *src; float *dst; int src_pitch, dst_pitch, width, rows; };

@@ -17,6 +17,9 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <unistd.h>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/meao.h"
 #include "common.cuh"
@@ -68,7 +71,7 @@ struct MeaoCtx {
 
     MeaoParams params;
     MeaoCamera camera;
-    MeaoVariants variants = {0, 0, 0};
+    MeaoVariants variants = {0, 0, 0, 0};
     bool plan_dirty = true;
     Plan plan;
 
@@ -96,11 +99,21 @@ struct MeaoCtx {
     bool compute_done_valid = false;
 
     bool tma_ok = false;
-    CUtensorMap map_low_ren[5];             // LowDepth<k> with the render box
+    CUtensorMap map_low_ren[kRenderTileVariants][5];    // LowDepth<k> with the render box of tile height kRenderTileHs[t]
     CUtensorMap map_low_ups[5];             // LowDepth<k> with the upsample depth box
     CUtensorMap map_ao_ups[5];              // lo AO of upsample lo level k (Occlusion4 / Combined k)
-    CUtensorMap map_low_wide[5];            // LowDepth<k> with the wide-render box
+    CUtensorMap map_low_wide[kRenderTileVariants][5];   // LowDepth<k> with the wide-render box
     CUtensorMap map_hq_ups[5];              // HighQuality<k> as LoResAO2 of upsample lo level k
+    CUtensorMap map_occ1_ups;               // Occlusion1 as LoResAO1 of the final upsample (MeaoVariants.single_scale)
+
+    // native neighbour exchange (meao_band_export / _connect / _step)
+    BandFlags *band_flags = nullptr;        // first 256 bytes of the arena
+    void *peer_base[2] = {nullptr, nullptr};    // the neighbours' arenas through a peer mapping (same layout as ours)
+    bool peer_ipc[2] = {false, false};      // mapping came from cudaIpcOpenMemHandle (must be closed)
+    unsigned long long band_timeout_ns = 2000000000ull;
+    uint32_t *host_error = nullptr;         // pinned + mapped: the exchange kernel mirrors its sticky error here (read by meao_band_step without a CUDA call)
+    uint32_t *host_error_dev = nullptr;     // device alias of host_error
+    int pdl_level = -1;                     // programmatic dependent launch in the captured graphs: -1 untried, 0 none, 1 plain chains, 2 all same-stream edges
 
     // row ranges (per level) for this band
     Range need_c[5];                        // rows of Occlusion<k>/Combined<k> to produce (k=1..4); [0] = final rows
@@ -109,11 +122,17 @@ struct MeaoCtx {
 
     int64_t launches = 0;
 
-    // CUDA graph cache: one instantiated graph per (depth, out, kind); dropped whenever the plan changes
+    // CUDA graph cache: one instantiated graph per (depth, out, kind), LRU; when it is full the least recently used
+    // executable graph is RE-TARGETED in place with cudaGraphExecUpdate (same topology, new pointers: no device
+    // synchronisation, launches already enqueued are unaffected).  Dropped as a whole only when the plan changes.
     struct GraphKey { const void *p[4]; int kind; bool operator<(const GraphKey &o) const {
         for (int i = 0; i < 4; i++) if (p[i] != o.p[i]) return p[i] < o.p[i];
         return kind < o.kind; } };
-    std::map<GraphKey, cudaGraphExec_t> graphs;
+    struct GraphEntry { cudaGraphExec_t exec; uint64_t last_use; };
+    std::map<GraphKey, GraphEntry> graphs;
+    std::vector<cudaGraphExec_t> retired;   // executable graphs replaced while possibly in flight: destroyed at the next drop_graph
+    uint64_t graph_clock = 0;
+    bool graphs_stale = false;              // set by the device-less getters: dropped by the next ensure_ready (on the right device)
     void *last_out = nullptr;               // where the last final upsample wrote (nullptr: c->result)
     int last_kind = MEAO_DEPTH_RAW_F32;     // ingest kind of the last downsample (selects the atlas padding value)
 
@@ -212,17 +231,31 @@ void build_plan(MeaoCtx *c)
     c->plan_dirty = false;
 }
 
+// Caller must have made c->device current (ensure_ready / meao_resize / meao_destroy do).
 void drop_graph(MeaoCtx *c)
 {
-    if (c->graphs.empty()) return;
+    c->graphs_stale = false;
+    if (c->graphs.empty() && c->retired.empty()) return;
     cudaDeviceSynchronize();            // a re-plan is rare; never destroy an executable graph that may still be in flight
-    for (auto &kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto &kv : c->graphs) cudaGraphExecDestroy(kv.second.exec);
+    for (auto ge : c->retired) cudaGraphExecDestroy(ge);
     c->graphs.clear();
+    c->retired.clear();
+}
+
+void disconnect_peers(MeaoCtx *c)
+{
+    for (int side = 0; side < 2; side++) {
+        if (c->peer_base[side] && c->peer_ipc[side]) cudaIpcCloseMemHandle(c->peer_base[side]);
+        c->peer_base[side] = nullptr; c->peer_ipc[side] = false;
+    }
 }
 
 void free_buffers(MeaoCtx *c)
 {
     drop_graph(c);
+    disconnect_peers(c);
+    c->band_flags = nullptr;
     if (c->arena) cudaFree(c->arena);
     c->arena = nullptr; c->arena_bytes = 0;
     c->depth_stage[0] = c->depth_stage[1] = nullptr; c->ao_stage[0] = c->ao_stage[1] = nullptr;
@@ -307,6 +340,7 @@ int allocate(MeaoCtx *c)
     c->result_pitch = align_up(c->lw[0], 128);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    take(sizeof(BandFlags));            // offset 0 in EVERY context's arena (the neighbours address it through their peer mapping)
     size_t o_lin = take((size_t)c->lin_pitch * c->lh[0] * sizeof(__half));
     size_t o_res = take((size_t)c->result_pitch * c->lh[0]);
     size_t o_low[5], o_occ[5], o_comb[4], o_hq[5];
@@ -327,6 +361,12 @@ int allocate(MeaoCtx *c)
     CUDA_TRY(c, cudaMemsetAsync(c->arena, 0, off, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     char *b = (char *)c->arena;
+    c->band_flags = (BandFlags *)b;
+    {
+        BandFlags init{}; init.epoch = 1;
+        CUDA_TRY(c, cudaMemcpy(c->band_flags, &init, sizeof init, cudaMemcpyHostToDevice));
+        if (c->host_error) *c->host_error = 0;
+    }
     c->lin = (__half *)(b + o_lin);
     c->result = (uint8_t *)(b + o_res);
     for (int k = 1; k <= 4; k++) {
@@ -341,16 +381,20 @@ int allocate(MeaoCtx *c)
     if (c->encode) {
         bool ok = true;
         for (int k = 1; k <= 4 && ok; k++) {
-            ok &= make_map(c, &c->map_low_ren[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], kRenderBoxW, kRenderBoxH) == 0;
+            for (int t = 0; t < kRenderTileVariants; t++) {
+                ok &= make_map(c, &c->map_low_ren[t][k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], kRenderBoxW, render_box_h(kRenderTileHs[t], false)) == 0;
+                ok &= make_map(c, &c->map_low_wide[t][k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], kRenderWideBoxW, render_box_h(kRenderTileHs[t], true)) == 0;
+            }
             ok &= make_map(c, &c->map_low_ups[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], kUpsDepthBoxW, kUpsDepthBoxH) == 0;
             uint8_t *ao = (k == 4) ? c->occ[4] : c->comb[k];
             ok &= make_map(c, &c->map_ao_ups[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ao, c->lw[k], c->lh[k], c->occ_pitch[k], kUpsAoBoxW, kUpsAoBoxH) == 0;
-            ok &= make_map(c, &c->map_low_wide[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->low[k], c->lw[k], c->lh[k], c->low_pitch[k], kRenderWideBoxW, kRenderWideBoxH) == 0;
             ok &= make_map(c, &c->map_hq_ups[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c->hq[k], c->lw[k], c->lh[k], c->occ_pitch[k], kUpsAoBoxW, kUpsAoBoxH) == 0;
         }
+        ok &= make_map(c, &c->map_occ1_ups, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c->occ[1], c->lw[1], c->lh[1], c->occ_pitch[1], kUpsAoBoxW, kUpsAoBoxH) == 0;
         c->tma_ok = ok;
     }
     if (!c->tma_ok) {
+        memset(&c->map_occ1_ups, 0, sizeof c->map_occ1_ups);
         memset(c->map_low_ren, 0, sizeof c->map_low_ren);
         memset(c->map_low_ups, 0, sizeof c->map_low_ups);
         memset(c->map_ao_ups, 0, sizeof c->map_ao_ups);
@@ -366,8 +410,25 @@ int ensure_ready(MeaoCtx *c)
     if (c->W <= 0) return fail(c, MEAO_ERR_INVALID, "meao_resize has not been called");
     if (c->plan_only) return fail(c, MEAO_ERR_CUDA, "plan-only context (device < 0): no CUDA device bound, and libmeao has no CPU fallback");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    if (c->plan_dirty) { build_plan(c); drop_graph(c); }
+    if (c->plan_dirty) { build_plan(c); c->graphs_stale = true; }
+    if (c->graphs_stale) drop_graph(c);
     return 0;
+}
+
+struct NvtxRange { explicit NvtxRange(const char *n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } };
+
+// Tile-height variant (index into kRenderTileHs = {32, 16, 8}) of a render launch.  The big levels keep the 64 x 32 tile
+// (least apron overhead: throughput); a level whose grid would not put two CTAs on every SM is latency-bound -- one
+// CTA's serial time IS the kernel time -- so it takes the tallest tile that still gives >= 2 x 148 CTAs, else 64 x 8.
+int render_tile_variant(const MeaoCtx *c, int k, int rows)
+{
+    const char *force = getenv("MEAO_REN_TILE");               // tuning aid: 0 / 1 / 2 forces a variant for every level
+    if (force && force[0] >= '0' && force[0] < '0' + kRenderTileVariants) return force[0] - '0';
+    for (int t = 0; t < kRenderTileVariants; t++) {
+        const int ctas = ((c->lw[k] + 63) / 64) * ((rows + kRenderTileHs[t] - 1) / kRenderTileHs[t]);
+        if (ctas >= 2 * 148) return t;
+    }
+    return kRenderTileVariants - 1;
 }
 
 // ---- the three recorders ---------------------------------------------------------------------
@@ -375,6 +436,8 @@ int ensure_ready(MeaoCtx *c)
 // PushDownsampleCommands, AO.cs:604-658
 int record_downsample(MeaoCtx *c, const void *depth, int kind, cudaStream_t s)
 {
+    if (kind < MEAO_DEPTH_RAW_F32 || kind > MEAO_DEPTH_RAW_D24S8) return fail(c, MEAO_ERR_INVALID, "bad depth kind %d", kind);
+    NvtxRange nv("meao::prepare_depth");
     PrepareArgs a{};
     a.depth = depth;
     a.in_format = (kind == MEAO_DEPTH_RAW_D16_UNORM) ? 1 : (kind == MEAO_DEPTH_RAW_D24S8 ? 2 : 0);
@@ -402,6 +465,7 @@ int record_render(MeaoCtx *c, int k, int kind, cudaStream_t s, bool wide = false
     const bool exh = c->variants.sample_exhaustively != 0;
     const int n = exh ? 12 : 7;
     const int *idx = exh ? idx_exh : idx_checker;
+    NvtxRange nv(wide ? "meao::render_ao_wide" : "meao::render_ao");
     RenderArgs a{};
     a.low = c->low[k]; a.lw = c->lw[k]; a.lh = c->lh[k]; a.lpitch = c->low_pitch[k];
     a.occ = wide ? c->hq[k] : c->occ[k]; a.opitch = c->occ_pitch[k];
@@ -418,7 +482,9 @@ int record_render(MeaoCtx *c, int k, int kind, cudaStream_t s, bool wide = false
     a.row0 = c->need_c[k].lo; a.row1 = c->need_c[k].hi;
     a.wide = wide ? 1 : 0;
     a.exhaustive = exh ? 1 : 0;
-    CUDA_TRY(c, launch_render_ao(wide ? c->map_low_wide[k] : c->map_low_ren[k], c->tma_ok, a, s));
+    const int tv = render_tile_variant(c, k, a.row1 - (a.row0 & ~3));
+    a.tile_h = kRenderTileHs[tv];
+    CUDA_TRY(c, launch_render_ao(wide ? c->map_low_wide[tv][k] : c->map_low_ren[tv][k], c->tma_ok, a, s));
     c->launches++;
     return 0;
 }
@@ -428,9 +494,11 @@ inline bool hq_level(const MeaoCtx *c, int k) { return ((c->variants.high_qualit
 int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
 {
     const int hi = lo - 1;
+    NvtxRange nv("meao::blur_upsample");
+    const bool single = c->variants.single_scale != 0 && lo == 1;      // LoResAO1 = Occlusion1: no coarser level contributes
     UpsampleArgs a{};
     a.lo_depth = c->low[lo]; a.low = c->lw[lo]; a.loh = c->lh[lo]; a.lo_dpitch = c->low_pitch[lo];
-    a.lo_ao = (lo == 4) ? c->occ[4] : c->comb[lo]; a.lo_apitch = c->occ_pitch[lo];
+    a.lo_ao = single ? c->occ[1] : (lo == 4) ? c->occ[4] : c->comb[lo]; a.lo_apitch = c->occ_pitch[lo];
     if (hi == 0) { a.hi_depth = c->lin; a.hi_is_half = 1; a.hi_dpitch = c->lin_pitch; a.hi_ao = nullptr; a.hi_apitch = 0; }
     else { a.hi_depth = c->low[hi]; a.hi_is_half = 0; a.hi_dpitch = c->low_pitch[hi]; a.hi_ao = c->occ[hi]; a.hi_apitch = c->occ_pitch[hi]; }
     if (hi == 0) {
@@ -455,17 +523,31 @@ int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
     }
     a.row0 = c->need_c[hi].lo; a.row1 = c->need_c[hi].hi;
     const uint8_t *lo_ao2 = hq_level(c, lo) ? c->hq[lo] : nullptr;                   // kernels main_premin / main_premin_blendout
-    CUDA_TRY(c, launch_blur_upsample(c->map_low_ups[lo], c->map_ao_ups[lo], &c->map_hq_ups[lo], c->tma_ok, a, lo_ao2, c->occ_pitch[lo], s));
+    CUDA_TRY(c, launch_blur_upsample(c->map_low_ups[lo], single ? c->map_occ1_ups : c->map_ao_ups[lo], &c->map_hq_ups[lo], c->tma_ok, a, lo_ao2, c->occ_pitch[lo], s));
     c->launches++;
     return 0;
 }
 
+// RAII: launches issued while one of these is alive (and `on`) carry the programmatic-dependent-launch attribute.
+struct PdlScope { bool prev; explicit PdlScope(bool on) : prev(g_launch_pdl) { g_launch_pdl = on; } ~PdlScope() { g_launch_pdl = prev; } };
+
 // The same nine launches as record_frame, recorded as a DAG on forked streams (for graph capture): the four
 // render levels are independent, the coarse upsample chain 4->3->2 only needs Occlusion2..4,
 // and only the last two upsamples wait for the big level-1 render.
-int record_frame_dag(MeaoCtx *c, const void *depth, int kind, void *ao_out, cudaStream_t s, bool do_prepare = true)
+// pdl: 0 = plain edges; 1 = programmatic dependent launch on the kernels whose ONLY predecessor is the kernel before them in
+// the same stream; 2 = also on kernels that additionally wait for an event of another branch.  after_exchange: the node
+// before this DAG is the neighbour-exchange kernel, which spins on remote flags -- nothing may be scheduled "early" behind it
+// (a grid parked in griddepcontrol.wait holds SM resources that the neighbour band's kernels may need: see DESIGN.md 4).
+int record_frame_dag(MeaoCtx *c, const void *depth, int kind, void *ao_out, cudaStream_t s, bool do_prepare = true, int pdl = 0,
+                     bool after_exchange = false)
 {
     int rc;
+    if (c->variants.single_scale) {     // BASELINE.json configs[0]: Downsample1 -> Render level 1 -> final-style Upsample on Occlusion1
+        if (do_prepare && (rc = record_downsample(c, depth, kind, s))) return rc;
+        { PdlScope p(pdl >= 1 && !after_exchange); if ((rc = record_render(c, 1, kind, s))) return rc; }
+        { PdlScope p(pdl >= 1); if ((rc = record_upsample(c, 1, ao_out, s))) return rc; }
+        return 0;
+    }
     cudaStream_t b1 = c->branch[0], b2 = c->branch[1], b3 = c->branch[2];
     if (do_prepare && (rc = record_downsample(c, depth, kind, s))) return rc;
     CUDA_TRY(c, cudaEventRecord(c->ev[0], s));
@@ -473,24 +555,24 @@ int record_frame_dag(MeaoCtx *c, const void *depth, int kind, void *ao_out, cuda
     CUDA_TRY(c, cudaStreamWaitEvent(b2, c->ev[0], 0));
     CUDA_TRY(c, cudaStreamWaitEvent(b3, c->ev[0], 0));
     // the optional high-quality render of a level (kernel "main") rides on the branch of that level's interleaved render
-    if ((rc = record_render(c, 1, kind, s))) return rc;
-    if (hq_level(c, 1) && (rc = record_render(c, 1, kind, s, true))) return rc;
+    { PdlScope p(pdl >= 1 && !after_exchange); if ((rc = record_render(c, 1, kind, s))) return rc; }
+    { PdlScope p(pdl >= 1); if (hq_level(c, 1) && (rc = record_render(c, 1, kind, s, true))) return rc; }
     if ((rc = record_render(c, 2, kind, b1))) return rc;
-    if (hq_level(c, 2) && (rc = record_render(c, 2, kind, b1, true))) return rc;
+    { PdlScope p(pdl >= 1); if (hq_level(c, 2) && (rc = record_render(c, 2, kind, b1, true))) return rc; }
     CUDA_TRY(c, cudaEventRecord(c->ev[1], b1));
     if ((rc = record_render(c, 3, kind, b2))) return rc;
-    if (hq_level(c, 3) && (rc = record_render(c, 3, kind, b2, true))) return rc;
+    { PdlScope p(pdl >= 1); if (hq_level(c, 3) && (rc = record_render(c, 3, kind, b2, true))) return rc; }
     CUDA_TRY(c, cudaEventRecord(c->ev[2], b2));
     if ((rc = record_render(c, 4, kind, b3))) return rc;
-    if (hq_level(c, 4) && (rc = record_render(c, 4, kind, b3, true))) return rc;
+    { PdlScope p(pdl >= 1); if (hq_level(c, 4) && (rc = record_render(c, 4, kind, b3, true))) return rc; }
     CUDA_TRY(c, cudaStreamWaitEvent(b3, c->ev[2], 0));
-    if ((rc = record_upsample(c, 4, nullptr, b3))) return rc;
+    { PdlScope p(pdl >= 2); if ((rc = record_upsample(c, 4, nullptr, b3))) return rc; }
     CUDA_TRY(c, cudaStreamWaitEvent(b3, c->ev[1], 0));
-    if ((rc = record_upsample(c, 3, nullptr, b3))) return rc;
+    { PdlScope p(pdl >= 2); if ((rc = record_upsample(c, 3, nullptr, b3))) return rc; }
     CUDA_TRY(c, cudaEventRecord(c->ev[3], b3));
     CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev[3], 0));
-    if ((rc = record_upsample(c, 2, nullptr, s))) return rc;
-    if ((rc = record_upsample(c, 1, ao_out, s))) return rc;
+    { PdlScope p(pdl >= 2); if ((rc = record_upsample(c, 2, nullptr, s))) return rc; }
+    { PdlScope p(pdl >= 1); if ((rc = record_upsample(c, 1, ao_out, s))) return rc; }
     return 0;
 }
 
@@ -507,9 +589,10 @@ int record_frame(MeaoCtx *c, const void *depth, int kind, void *ao_out, cudaStre
     mark();
     if ((rc = record_downsample(c, depth, kind, s))) return rc;
     names.push_back("prepare_depth"); mark();
-    for (int k = 1; k <= 4; k++) { if ((rc = record_render(c, k, kind, s))) return rc; names.push_back(ren_names[k]); mark(); }
-    for (int k = 1; k <= 4; k++) if (hq_level(c, k)) { if ((rc = record_render(c, k, kind, s, true))) return rc; names.push_back(hq_names[k]); mark(); }
-    for (int lo = 4; lo >= 1; lo--) { if ((rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s))) return rc; names.push_back(ups_names[lo]); mark(); }
+    const int kmax = c->variants.single_scale ? 1 : 4;       // single-scale: Render level 1 + the final-style Upsample only
+    for (int k = 1; k <= kmax; k++) { if ((rc = record_render(c, k, kind, s))) return rc; names.push_back(ren_names[k]); mark(); }
+    for (int k = 1; k <= kmax; k++) if (hq_level(c, k)) { if ((rc = record_render(c, k, kind, s, true))) return rc; names.push_back(hq_names[k]); mark(); }
+    for (int lo = kmax; lo >= 1; lo--) { if ((rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s))) return rc; names.push_back(ups_names[lo]); mark(); }
     if (profile) {
         CUDA_TRY(c, cudaStreamSynchronize(s));
         c->last_profile.clear();
@@ -550,7 +633,7 @@ int buffer_ptr(MeaoCtx *c, int id, void **p, size_t *pitch_bytes)
 }
 
 std::mutex g_event_mutex;
-struct EventBinding { MeaoCtx *ctx; const void *depth; int kind; void *out; };
+struct EventBinding { MeaoCtx *ctx; const void *depth; int kind; void *out; void *stream; };
 std::map<int, EventBinding> g_events;
 
 }  // namespace
@@ -612,6 +695,11 @@ int meao_create(const MeaoDeviceCfg *cfg, MeaoCtx **out)
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete c; return fail(nullptr, MEAO_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    if (cudaHostAlloc((void **)&c->host_error, 64, cudaHostAllocMapped) == cudaSuccess) {
+        *c->host_error = 0;
+        if (cudaHostGetDevicePointer((void **)&c->host_error_dev, c->host_error, 0) != cudaSuccess) c->host_error_dev = nullptr;
+    } else c->host_error = nullptr;
+    cudaGetLastError();
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     const char *no_tma = getenv("MEAO_DISABLE_TMA");     // debugging aid: force the gather path in every tile
@@ -640,6 +728,7 @@ void meao_destroy(MeaoCtx *c)
     for (auto b : c->slot_stream) if (b) { cudaStreamSynchronize(b); cudaStreamDestroy(b); }
     for (auto e : c->slot_done) if (e) cudaEventDestroy(e);
     if (c->compute_done) cudaEventDestroy(c->compute_done);
+    if (c->host_error) cudaFreeHost(c->host_error);
     delete c;
 }
 
@@ -669,7 +758,8 @@ int meao_set_variants(MeaoCtx *c, const MeaoVariants *v)
 {
     if (!c || !v) return MEAO_ERR_INVALID;
     if (v->high_quality_mask < 0 || v->high_quality_mask > 15) return fail(c, MEAO_ERR_INVALID, "high_quality_mask %d not in 0..15", v->high_quality_mask);
-    MeaoVariants n{v->single_pass_stereo ? 1 : 0, v->sample_exhaustively ? 1 : 0, v->high_quality_mask};
+    if (v->single_scale && v->high_quality_mask) return fail(c, MEAO_ERR_INVALID, "single_scale excludes high_quality_mask");
+    MeaoVariants n{v->single_pass_stereo ? 1 : 0, v->sample_exhaustively ? 1 : 0, v->high_quality_mask, v->single_scale ? 1 : 0};
     const bool changed = memcmp(&c->variants, &n, sizeof n) != 0;
     c->variants = n;
     if (changed) c->plan_dirty = true;          // re-plan + drop the captured graphs (ensure_ready)
@@ -716,8 +806,22 @@ int meao_set_row_band(MeaoCtx *c, int32_t row0, int32_t row1, int32_t prev_row0,
         return fail(c, MEAO_ERR_INVALID, "bad neighbour extents");
     if ((row0 > 0) != (prev_row0 >= 0) || (row1 < c->H) != (next_row1 >= 0))
         return fail(c, MEAO_ERR_INVALID, "neighbour extents must be given exactly where the band is interior");
+    // validate against temporaries; the context keeps its old band when the new one is refused
+    {
+        const BandNeeds n = compute_needs(c, row0, row1);
+        for (int k = 1; k <= 4; k++) {
+            if (n.need_low[k].lo < n.own_low[k].lo && (prev_row0 < 0 || n.need_low[k].lo < (prev_row0 >> k)))
+                return fail(c, MEAO_ERR_UNSUPPORTED, "halo of level %d reaches beyond the band above", k);
+            if (n.need_low[k].hi > n.own_low[k].hi && (next_row1 < 0 || n.need_low[k].hi > ((next_row1 + (1 << k) - 1) >> k)))
+                return fail(c, MEAO_ERR_UNSUPPORTED, "halo of level %d reaches beyond the band below", k);
+        }
+    }
+    if (!c->plan_only) {
+        CUDA_TRY(c, cudaSetDevice(c->device));
+        drop_graph(c);
+        disconnect_peers(c);        // the halo ranges change: the host exports / connects again
+    }
     c->band0 = row0; c->band1 = row1; c->prev0 = prev_row0; c->next1 = next_row1;
-    drop_graph(c);
     return setup_band(c);
 }
 
@@ -834,29 +938,68 @@ static int halo_kernel(MeaoCtx *c, void *up, void *down, bool pack, cudaStream_t
     return 0;
 }
 
-// Graph-cached halves of a band step.  phase A: prepare_depth on the band + pack both halos (2 launches);
-// phase B: unpack both halos + 4 renders + 4 upsamples (9 launches, DAG).  The neighbour exchange happens between.
-static int band_graph(MeaoCtx *c, const MeaoCtx::GraphKey &key, cudaStream_t s, int nk, const std::function<int(cudaStream_t)> &record)
+// ---- graph cache ----------------------------------------------------------------------------------------------------
+// record(stream, pdl) issues the launches; it is captured into a graph, with the highest programmatic-dependent-launch
+// level the runtime accepts (tried once per context: 2, then 1, then 0 = plain edges).
+static int capture_graph(MeaoCtx *c, const std::function<int(cudaStream_t, int)> &record, cudaGraph_t *out)
 {
-    if (c->flags & MEAO_FLAG_NO_GRAPH) return record(s);
-    auto it = c->graphs.find(key);
-    if (it == c->graphs.end()) {
-        if (c->graphs.size() >= 64) drop_graph(c);
+    const char *env = getenv("MEAO_PDL");                           // tuning / debugging aid: cap the level (0 disables)
+    const int cap = (env && env[0] >= '0' && env[0] <= '2') ? env[0] - '0' : 2;
+    for (int level = (c->pdl_level >= 0 ? c->pdl_level : cap); level >= 0; level--) {
         cudaGraph_t g = nullptr;
         CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t before = c->launches;
-        int rc = record(c->stream);
+        const int rc = record(c->stream, level);
         c->launches = before;
-        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-        if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-        cudaGraphExec_t ge = nullptr;
-        e = cudaGraphInstantiate(&ge, g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
-        it = c->graphs.emplace(key, ge).first;
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (rc == 0 && e == cudaSuccess) { c->pdl_level = level; *out = g; return 0; }
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (level == 0) {
+            if (rc) return rc;
+            return fail(c, MEAO_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        }
+        // a capture that failed with PDL edges is retried one level lower (mixed programmatic + event dependencies may be refused)
     }
-    CUDA_TRY(c, cudaGraphLaunch(it->second, s));
+    return fail(c, MEAO_ERR_CUDA, "graph capture failed");
+}
+
+static int launch_cached(MeaoCtx *c, const MeaoCtx::GraphKey &key, cudaStream_t s, int nk, const std::function<int(cudaStream_t, int)> &record)
+{
+    if (c->flags & MEAO_FLAG_NO_GRAPH) return record(s, 0);
+    constexpr size_t kMaxGraphs = 64;
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+        cudaGraph_t g = nullptr;
+        int rc = capture_graph(c, record, &g);
+        if (rc) return rc;
+        cudaGraphExec_t ge = nullptr;
+        if (c->graphs.size() >= kMaxGraphs) {
+            // a caller that rotates more buffers than the cache holds: re-target the least recently used executable graph
+            // (same topology, new kernel arguments) instead of synchronising the device and instantiating again
+            auto victim = c->graphs.begin();
+            for (auto j = c->graphs.begin(); j != c->graphs.end(); ++j) if (j->second.last_use < victim->second.last_use) victim = j;
+            cudaGraphExecUpdateResultInfo info;
+            ge = victim->second.exec;
+            if (cudaGraphExecUpdate(ge, g, &info) != cudaSuccess) { cudaGetLastError(); c->retired.push_back(ge); ge = nullptr; }
+            c->graphs.erase(victim);
+        }
+        if (!ge) {
+            cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+            if (e != cudaSuccess && c->pdl_level > 0) {             // be conservative: fall back to plain edges once and for all
+                cudaGetLastError();
+                cudaGraphDestroy(g); g = nullptr;
+                c->pdl_level = 0;
+                if ((rc = capture_graph(c, record, &g))) return rc;
+                e = cudaGraphInstantiate(&ge, g, 0);
+            }
+            if (e != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(c, MEAO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+        }
+        cudaGraphDestroy(g);
+        it = c->graphs.emplace(key, MeaoCtx::GraphEntry{ge, 0}).first;
+    }
+    it->second.last_use = ++c->graph_clock;
+    CUDA_TRY(c, cudaGraphLaunch(it->second.exec, s));
     c->launches += nk;
     return 0;
 }
@@ -868,9 +1011,10 @@ int meao_band_phase_a(MeaoCtx *c, const void *depth, int32_t kind, void *send_up
     c->last_kind = kind;
     const MeaoCtx::GraphKey key{{depth, send_up, send_down, nullptr}, 100 + kind};
     const int nk = 1 + ((send_up || send_down) ? 1 : 0);
-    return band_graph(c, key, (cudaStream_t)stream, nk, [&](cudaStream_t s) {
+    return launch_cached(c, key, (cudaStream_t)stream, nk, [&](cudaStream_t s, int pdl) {
         int r = record_downsample(c, depth, kind, s);
         if (r) return r;
+        PdlScope p(pdl >= 1);
         return halo_kernel(c, send_up, send_down, true, s);
     });
 }
@@ -883,11 +1027,139 @@ int meao_band_phase_b(MeaoCtx *c, const void *recv_up, const void *recv_down, vo
     const MeaoCtx::GraphKey key{{recv_up, recv_down, ao_out, nullptr}, 200 + kind};
     const int nk = meao_kernels_per_frame(c) - 1 + ((recv_up || recv_down) ? 1 : 0);
     c->last_out = ao_out;
-    return band_graph(c, key, (cudaStream_t)stream, nk, [&](cudaStream_t s) {
+    return launch_cached(c, key, (cudaStream_t)stream, nk, [&](cudaStream_t s, int pdl) {
         int r = halo_kernel(c, (void *)recv_up, (void *)recv_down, false, s);
         if (r) return r;
-        return record_frame_dag(c, nullptr, kind, ao_out, s, false);
+        return record_frame_dag(c, nullptr, kind, ao_out, s, false, pdl);
     });
+}
+
+// ---- native neighbour exchange (include/meao.h) -----------------------------------------------------------------------
+namespace {
+struct PeerHandlePod {              // what MeaoPeerHandle carries (<= MEAO_PEER_HANDLE_BYTES)
+    uint32_t magic;                 // 'MEAO'
+    int32_t device;
+    int64_t pid;
+    int32_t W, H;
+    uint64_t arena_bytes;
+    uint64_t arena_ptr;             // valid in the exporting process only
+    cudaIpcMemHandle_t ipc;         // valid in every other process on this node
+};
+static_assert(sizeof(PeerHandlePod) <= MEAO_PEER_HANDLE_BYTES, "MeaoPeerHandle too small");
+constexpr uint32_t kPeerMagic = 0x4d45414fu;
+}  // namespace
+
+int meao_band_export(MeaoCtx *c, MeaoPeerHandle *out)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!out) return fail(c, MEAO_ERR_INVALID, "out is NULL");
+    PeerHandlePod h{};
+    h.magic = kPeerMagic; h.device = c->device; h.pid = (int64_t)getpid(); h.W = c->W; h.H = c->H;
+    h.arena_bytes = c->arena_bytes; h.arena_ptr = (uint64_t)(uintptr_t)c->arena;
+    const cudaError_t e = cudaIpcGetMemHandle(&h.ipc, c->arena);
+    if (e != cudaSuccess) { cudaGetLastError(); memset(&h.ipc, 0, sizeof h.ipc); }     // in-process peers still work without IPC
+    memset(out, 0, sizeof *out);
+    memcpy(out->bytes, &h, sizeof h);
+    return MEAO_OK;
+}
+
+int meao_band_connect(MeaoCtx *c, int32_t side, const MeaoPeerHandle *peer)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (side != 0 && side != 1) return fail(c, MEAO_ERR_INVALID, "side must be 0 (up) or 1 (down)");
+    drop_graph(c);                                  // captured band steps carry the old peer pointers
+    if (c->peer_base[side] && c->peer_ipc[side]) cudaIpcCloseMemHandle(c->peer_base[side]);
+    c->peer_base[side] = nullptr; c->peer_ipc[side] = false;
+    if (!peer) return MEAO_OK;
+    if ((side == 0 && c->prev0 < 0) || (side == 1 && c->next1 < 0)) return fail(c, MEAO_ERR_INVALID, "this band has no neighbour on side %d", side);
+    PeerHandlePod h;
+    memcpy(&h, peer->bytes, sizeof h);
+    if (h.magic != kPeerMagic) return fail(c, MEAO_ERR_INVALID, "not a MeaoPeerHandle");
+    if (h.W != c->W || h.H != c->H || h.arena_bytes != c->arena_bytes)
+        return fail(c, MEAO_ERR_INVALID, "neighbour frame %dx%d (arena %llu B) differs from this context's %dx%d (%zu B)", h.W, h.H,
+                    (unsigned long long)h.arena_bytes, c->W, c->H, c->arena_bytes);
+    if (h.pid == (int64_t)getpid()) {
+        if (h.device != c->device) {
+            int can = 0;
+            CUDA_TRY(c, cudaDeviceCanAccessPeer(&can, c->device, h.device));
+            if (!can) return fail(c, MEAO_ERR_UNSUPPORTED, "device %d cannot access device %d", c->device, h.device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(c, MEAO_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        c->peer_base[side] = (void *)(uintptr_t)h.arena_ptr;
+    } else {
+        void *p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, MEAO_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); }
+        c->peer_base[side] = p; c->peer_ipc[side] = true;
+    }
+    const char *t = getenv("MEAO_BAND_TIMEOUT_MS");
+    if (t && atof(t) > 0) c->band_timeout_ns = (unsigned long long)(atof(t) * 1e6);
+    return MEAO_OK;
+}
+
+// prepare_depth on the band has run: push my border rows into the neighbours' LowDepth1..4, signal, wait for theirs
+static int record_exchange(MeaoCtx *c, cudaStream_t s)
+{
+    NvtxRange nv("meao::band_exchange");
+    XchgArgs a{}; a.nseg = 0;
+    a.local = c->band_flags;
+    a.host_error = c->host_error_dev;
+    a.timeout_ns = c->band_timeout_ns;
+    for (int side = 0; side < 2; side++) {
+        a.peer[side] = (BandFlags *)c->peer_base[side];                 // BandFlags sit at offset 0 of every arena
+        if (!c->peer_base[side]) continue;
+        Range r[5]; halo_ranges(c, side, true, r);
+        for (int k = 1; k <= 4; k++) {
+            const int rows = r[k].hi - r[k].lo;
+            if (rows <= 0) continue;
+            const size_t off = (size_t)((char *)(c->low[k] + (size_t)r[k].lo * c->low_pitch[k]) - (char *)c->arena);
+            const size_t bytes = (size_t)rows * c->low_pitch[k] * sizeof(float);          // whole pitched rows: contiguous, 128 B aligned
+            XchgSeg &g = a.seg[a.nseg++];
+            g.src = (const uint4 *)((char *)c->arena + off);
+            g.dst = (uint4 *)((char *)c->peer_base[side] + off);
+            g.n16 = (uint32_t)(bytes / 16); g.side = side;
+        }
+    }
+    if (a.nseg == 0) return 0;
+    CUDA_TRY(c, launch_band_exchange(a, s));
+    c->launches++;
+    return 0;
+}
+
+int meao_band_step(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void *stream)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!depth || !ao_out) return fail(c, MEAO_ERR_INVALID, "depth / ao_out is NULL");
+    if ((c->prev0 >= 0 && !c->peer_base[0]) || (c->next1 >= 0 && !c->peer_base[1]))
+        return fail(c, MEAO_ERR_INVALID, "meao_band_step: connect every neighbour first (meao_band_export / meao_band_connect)");
+    // a time-out of an earlier step is sticky; the kernel mirrors it into a mapped host word, so this costs no CUDA call
+    if (c->host_error && *(volatile uint32_t *)c->host_error != 0)
+        return fail(c, MEAO_ERR_PEER, "neighbour exchange timed out earlier (error %u): see meao_band_status", *(volatile uint32_t *)c->host_error);
+    NvtxRange nv("meao::band_step");
+    c->last_kind = kind; c->last_out = ao_out;
+    const MeaoCtx::GraphKey key{{depth, ao_out, c->peer_base[0], c->peer_base[1]}, 300 + kind};
+    const bool has_peer = c->peer_base[0] || c->peer_base[1];
+    const int nk = meao_kernels_per_frame(c) + (has_peer ? 1 : 0);
+    return launch_cached(c, key, (cudaStream_t)stream, nk, [&](cudaStream_t s, int pdl) {
+        int r = record_downsample(c, depth, kind, s);
+        if (r) return r;
+        { PdlScope p(pdl >= 1); if ((r = record_exchange(c, s))) return r; }
+        return record_frame_dag(c, nullptr, kind, ao_out, s, false, pdl, has_peer);
+    });
+}
+
+int meao_band_status(MeaoCtx *c, int32_t out4[4])
+{
+    if (!c || !out4 || c->plan_only || !c->band_flags) return MEAO_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    BandFlags f{};
+    // a dedicated non-blocking stream: never waits for (or delays) the frames in flight
+    CUDA_TRY(c, cudaMemcpyAsync(&f, c->band_flags, sizeof f, cudaMemcpyDeviceToHost, c->slot_stream[1]));
+    CUDA_TRY(c, cudaStreamSynchronize(c->slot_stream[1]));
+    out4[0] = (int32_t)f.epoch; out4[1] = (int32_t)f.error; out4[2] = c->peer_base[0] ? 1 : 0; out4[3] = c->peer_base[1] ? 1 : 0;
+    return MEAO_OK;
 }
 
 int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void *stream)
@@ -902,28 +1174,12 @@ int meao_render(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, void 
 
     // plan-once / replay: one captured graph per (depth, out, kind), like the reference's command buffer
     // that is re-recorded only when something changed (AO.cs:334-347)
+    NvtxRange nv("meao::frame");
     const MeaoCtx::GraphKey key{{depth, ao_out, nullptr, nullptr}, kind};
-    auto it = c->graphs.find(key);
-    if (it == c->graphs.end()) {
-        if (c->graphs.size() >= 64) drop_graph(c);
-        cudaGraph_t g = nullptr;
-        CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        const int64_t before = c->launches;
-        rc = record_frame_dag(c, depth, kind, ao_out, c->stream);
-        c->launches = before;
-        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-        if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-        cudaGraphExec_t ge = nullptr;
-        e = cudaGraphInstantiate(&ge, g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
-        it = c->graphs.emplace(key, ge).first;
-    }
     c->last_kind = kind; c->last_out = ao_out;
-    CUDA_TRY(c, cudaGraphLaunch(it->second, s));
-    c->launches += meao_kernels_per_frame(c);
-    return MEAO_OK;
+    return launch_cached(c, key, s, meao_kernels_per_frame(c), [&](cudaStream_t cs, int pdl) {
+        return record_frame_dag(c, depth, kind, ao_out, cs, true, pdl);
+    });
 }
 
 int meao_render_host_async(MeaoCtx *c, const void *depth_host, int32_t kind, uint8_t *ao_host, int32_t slot)
@@ -1102,7 +1358,7 @@ int meao_set_buffer(MeaoCtx *c, int32_t id, const void *host_in, size_t host_byt
 static int plan_only(MeaoCtx *c)
 {
     if (!c || c->W <= 0) return MEAO_ERR_INVALID;
-    if (c->plan_dirty) { build_plan(c); drop_graph(c); }
+    if (c->plan_dirty) { build_plan(c); c->graphs_stale = true; }    // the captured graphs are dropped by the next ensure_ready, on c->device
     return 0;
 }
 
@@ -1182,12 +1438,12 @@ int meao_composite_debug(MeaoCtx *c, const void *view, void *color, int32_t fmt,
     return MEAO_OK;
 }
 
-int meao_bind_event(MeaoCtx *c, int32_t event_id, const void *depth, int32_t kind, void *ao_out)
+int meao_bind_event(MeaoCtx *c, int32_t event_id, const void *depth, int32_t kind, void *ao_out, void *stream)
 {
     if (!c) return MEAO_ERR_INVALID;
     std::lock_guard<std::mutex> g(g_event_mutex);
     if (!depth && !ao_out) { g_events.erase(event_id); return MEAO_OK; }
-    g_events[event_id] = EventBinding{c, depth, kind, ao_out};
+    g_events[event_id] = EventBinding{c, depth, kind, ao_out, stream};
     return MEAO_OK;
 }
 
@@ -1200,14 +1456,16 @@ void meao_render_event(int event_id)
         if (it == g_events.end()) return;
         b = it->second;
     }
-    meao_render(b.ctx, b.depth, b.kind, b.out, nullptr);
+    meao_render(b.ctx, b.depth, b.kind, b.out, b.stream);
 }
 
 MeaoRenderEventFunc meao_get_render_event_func(void) { return meao_render_event; }
 
 int64_t meao_launch_count(const MeaoCtx *c) { return c ? c->launches : 0; }
+int meao_pdl_level(const MeaoCtx *c) { return c ? c->pdl_level : -1; }
 int meao_kernels_per_frame(const MeaoCtx *c)
 {
+    if (c && c->variants.single_scale) return 3;      // Downsample1 + Render level 1 + the final-style Upsample
     int n = 9;
     if (c) for (int k = 1; k <= 4; k++) n += hq_level(c, k) ? 1 : 0;
     return n;

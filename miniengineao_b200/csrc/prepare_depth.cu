@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_depth_kernel(const Prepa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = blockIdx.x * kPrepTileW + lane * 8;
     const int ybase = a.row0 + blockIdx.y * kPrepTileH;
+    pdl_wait();                     // (first node of the frame's graph: a no-op today; keeps the rule "wait before the first global access")
+    pdl_launch_dependents();
     if (x >= a.W) return;
     const bool full = a.vec_ok && (x + 8 <= a.W);
 

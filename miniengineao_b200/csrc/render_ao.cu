@@ -32,29 +32,25 @@ namespace meao {
 
 namespace {
 
-#ifndef MEAO_REN_TH
-#define MEAO_REN_TH 32
-#endif
 #ifndef MEAO_REN_THREADS
 #define MEAO_REN_THREADS 256
 #endif
-constexpr int kTW = 64, kTH = MEAO_REN_TH;  // outputs per CTA (64x32 / 256 threads measured 2 % faster than 64x16 / 128 in the 3-stream frame pipeline)
+constexpr int kTW = 64;                     // outputs per CTA: 64 x TH, TH = 32 (64x32 / 256 threads measured 2 % faster than 64x16 / 128 in the
+                                            // 3-stream frame pipeline), 16 or 8 for the latency-bound coarse levels (kernels.h kRenderTileHs)
 // MODE 0 (main_interleaved): apron 4 slice texels x stride 4 = 16; MODE 1 (main, wide): apron 4 taps x stride 2 = 8
-template <int MODE> struct Geo {
-    static constexpr int kStride = MODE == 0 ? 4 : 2;
+template <int MODE> constexpr int kTapStride = MODE == 0 ? 4 : 2;
+template <int MODE, int TH> struct Geo {
     static constexpr int kAp = MODE == 0 ? 16 : 8;
     static constexpr int kSW = kTW + 2 * kAp;       // 96 == kRenderBoxW      | 80 == kRenderWideBoxW
-    static constexpr int kSH = kTH + 2 * kAp;       // 64 == kRenderBoxH      | 48 == kRenderWideBoxH
+    static constexpr int kSH = TH + 2 * kAp;        // == render_box_h(TH, MODE == 1)
 };
 #ifndef MEAO_REN_MINB
 #define MEAO_REN_MINB 4
 #endif
 constexpr int kThreads = MEAO_REN_THREADS;
 constexpr int kWarps = kThreads / 32;
-static_assert((Geo<0>::kSW * Geo<0>::kSH / 4) % kThreads == 0, "tile must split evenly over the threads");
-static_assert(Geo<0>::kSW == kRenderBoxW && Geo<0>::kSH == kRenderBoxH, "TMA box mismatch");
-static_assert(Geo<1>::kSW == kRenderWideBoxW && Geo<1>::kSH == kRenderWideBoxH, "TMA box mismatch (wide)");
-static_assert(kTH % kWarps == 0, "rows must split evenly over the warps");
+static_assert(Geo<0, 32>::kSW == kRenderBoxW && Geo<1, 32>::kSW == kRenderWideBoxW, "TMA box mismatch");
+static_assert(Geo<0, 32>::kSH == render_box_h(32, false) && Geo<1, 8>::kSH == render_box_h(8, true), "TMA box mismatch");
 
 // Render.compute:60-75 for one sample pair, TWO horizontally adjacent pixels at once (.x / .y lanes).
 //   * clamp(d, p, 1) == max(saturate(d), p) for p in [0,1], including d = NaN/+-inf (HLSL min/max return
@@ -91,7 +87,7 @@ __device__ __forceinline__ float2 pair_eval2(float2 S1, float2 S2, float2 inv_ra
 template <int MODE, int DX, int DY>
 __device__ __forceinline__ float2 pair2(const float *c, float2 ir, float2 nf, float rf)
 {
-    constexpr int OFF = (Geo<MODE>::kStride * DY) * Geo<MODE>::kSW + Geo<MODE>::kStride * DX;
+    constexpr int OFF = (kTapStride<MODE> * DY) * Geo<MODE, 32>::kSW + kTapStride<MODE> * DX;    // the tile width does not depend on TH
     const float2 s1 = *reinterpret_cast<const float2 *>(c + OFF);
     const float2 s2 = *reinterpret_cast<const float2 *>(c - OFF);
     return pair_eval2(s1, s2, ir, nf, rf);
@@ -128,12 +124,14 @@ __device__ __forceinline__ void lshape2(const float *c, float2 inv, float it, fl
     ao = __ffma2_rn(make_float2(w, w), __fmul2_rn(make_float2(0.25f, 0.25f), t), ao);
 }
 
-template <int MODE, bool EXH>
+template <int MODE, bool EXH, int TH>
 __global__ void __launch_bounds__(kThreads, MEAO_REN_MINB)
 render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a, const int use_tma)
 {
 #ifdef MEAO_DEVICE_OK
-    constexpr int kAp = Geo<MODE>::kAp, kSW = Geo<MODE>::kSW, kSH = Geo<MODE>::kSH;
+    static_assert(TH % kWarps == 0, "rows must split evenly over the warps");
+    constexpr int kTH = TH;
+    constexpr int kAp = Geo<MODE, TH>::kAp, kSW = Geo<MODE, TH>::kSW, kSH = Geo<MODE, TH>::kSH;
 #ifdef MEAO_EMULATE
     float *tile = reinterpret_cast<float *>(meao_emu::dynamic_smem());
 #else
@@ -147,6 +145,8 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
 
     const bool interior = use_tma && (X0 - kAp >= 0) && (Y0 - kAp >= 0) && (X0 + kTW + kAp <= a.lw) && (Y0 + kTH + kAp <= a.lh);
 
+    pdl_wait();                     // LowDepth<k> comes from the preceding grid(s); nothing above touches global memory
+    pdl_launch_dependents();
     if (interior) {
         // ---- TMA: one 96x64 (wide: 80x48) f32 box, completion on an mbarrier ------------------
         if (tid == 0) {
@@ -162,8 +162,10 @@ render_ao_kernel(const __grid_constant__ CUtensorMap low_map, const RenderArgs a
         if (MODE == 0) {
             // in-place f16 rounding (what the RHalf atlas store of DS1:71 / DS2:41 does)
             float4 *t4 = reinterpret_cast<float4 *>(tile);
+            constexpr int kQuads = kSW * kSH / 4;
 #pragma unroll
-            for (int i = 0; i < (kSW * kSH / 4) / kThreads; i++) {
+            for (int i = 0; i < (kQuads + kThreads - 1) / kThreads; i++) {
+                if (kQuads % kThreads != 0 && tid + i * kThreads >= kQuads) break;
                 float4 q = t4[tid + i * kThreads];
                 q.x = f16_round(q.x); q.y = f16_round(q.y); q.z = f16_round(q.z); q.w = f16_round(q.w);
                 t4[tid + i * kThreads] = q;
@@ -260,22 +262,32 @@ __global__ void synth_tiled_kernel(const float *low, int lw, int lh, int lpitch,
 
 }  // namespace
 
+template <int MODE, bool EXH, int TH>
+static void launch_render_variant(const CUtensorMap &low_map, int t, const RenderArgs &a, dim3 grid, cudaStream_t s)
+{
+    const size_t smem = (size_t)Geo<MODE, TH>::kSW * Geo<MODE, TH>::kSH * sizeof(float);
+    MEAO_LAUNCH((render_ao_kernel<MODE, EXH, TH>), grid, kThreads, smem, s, low_map, a, t);
+}
+template <int MODE, bool EXH>
+static cudaError_t launch_render_th(const CUtensorMap &low_map, int t, const RenderArgs &a, int gx, int rows, cudaStream_t s)
+{
+    switch (a.tile_h) {
+        case kRenderTileHs[0]: launch_render_variant<MODE, EXH, kRenderTileHs[0]>(low_map, t, a, dim3(gx, ceil_div(rows, kRenderTileHs[0])), s); break;
+        case kRenderTileHs[1]: launch_render_variant<MODE, EXH, kRenderTileHs[1]>(low_map, t, a, dim3(gx, ceil_div(rows, kRenderTileHs[1])), s); break;
+        case kRenderTileHs[2]: launch_render_variant<MODE, EXH, kRenderTileHs[2]>(low_map, t, a, dim3(gx, ceil_div(rows, kRenderTileHs[2])), s); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_render_ao(const CUtensorMap &low_map, bool use_tma, const RenderArgs &a, cudaStream_t s)
 {
     if (a.row1 <= a.row0) return cudaSuccess;
     const int ybase = a.row0 & ~3;
-    dim3 grid(ceil_div(a.lw, kTW), ceil_div(a.row1 - ybase, kTH));
+    const int gx = ceil_div(a.lw, kTW), rows = a.row1 - ybase;
     const int t = use_tma ? 1 : 0;
-    if (!a.wide) {
-        const size_t smem = (size_t)Geo<0>::kSW * Geo<0>::kSH * sizeof(float);
-        if (!a.exhaustive) MEAO_LAUNCH((render_ao_kernel<0, false>), grid, kThreads, smem, s, low_map, a, t);
-        else               MEAO_LAUNCH((render_ao_kernel<0, true>), grid, kThreads, smem, s, low_map, a, t);
-    } else {
-        const size_t smem = (size_t)Geo<1>::kSW * Geo<1>::kSH * sizeof(float);
-        if (!a.exhaustive) MEAO_LAUNCH((render_ao_kernel<1, false>), grid, kThreads, smem, s, low_map, a, t);
-        else               MEAO_LAUNCH((render_ao_kernel<1, true>), grid, kThreads, smem, s, low_map, a, t);
-    }
-    return cudaGetLastError();
+    if (!a.wide) return a.exhaustive ? launch_render_th<0, true>(low_map, t, a, gx, rows, s) : launch_render_th<0, false>(low_map, t, a, gx, rows, s);
+    return a.exhaustive ? launch_render_th<1, true>(low_map, t, a, gx, rows, s) : launch_render_th<1, false>(low_map, t, a, gx, rows, s);
 }
 
 cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int sw, int sh, float pad,

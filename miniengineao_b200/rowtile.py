@@ -2,7 +2,14 @@
 does not have -- SURVEY.md 8e).
 
 One process per GPU.  Rank r owns output rows [cuts[r], cuts[r+1]) (16-row aligned) and only ever sees that
-band of the raw depth.  Per frame:
+band of the raw depth.
+
+mode "native" (default on GPUs): the exchange lives INSIDE libmeao (include/meao.h "native neighbour exchange"): the
+ranks swap arena handles once (meao_band_export -> all_gather -> meao_band_connect: cudaIpc peer mappings), after which a
+step is ONE CUDA graph per band -- prepare_depth -> band_exchange_kernel (peer stores over NVLink + epoch flags) ->
+render x4 + upsample x4 -- with no Python, no NCCL call and no staging copy between the phases.
+
+mode "p2p" (the CPU / gloo tests, and the fallback when peer mappings are unavailable).  Per frame:
 
     phase A  (one CUDA graph)  prepare_depth on the own rows (LinearDepth + LowDepth1..4)
                                + pack of the border rows of LowDepth1..4 each neighbour needs (<= ~0.6 MB per side at 8K)
@@ -56,10 +63,10 @@ def exchange(send_up, send_down, recv_up, recv_down, rank: int, world: int, grou
 class RowTiledAO:
     """GPU driver of one band (one per rank)."""
 
-    def __init__(self, camera, rank: int, world: int, device: int, **params):
+    def __init__(self, camera, rank: int, world: int, device: int, mode: str = "native", group=None, **params):
         import torch
         from .ambient_occlusion import AmbientOcclusion
-        self.rank, self.world = rank, world
+        self.rank, self.world, self.mode, self.group = rank, world, mode, group
         self.cuts = partition(camera.pixelHeight, world)
         self.row0, self.row1 = self.cuts[rank], self.cuts[rank + 1]
         self.ao = AmbientOcclusion(camera, device=device)
@@ -72,6 +79,24 @@ class RowTiledAO:
         self.send = [mk(self.ao.halo_bytes(0)), mk(self.ao.halo_bytes(1))]
         self.recv = [mk(self.ao.halo_recv_bytes(0)), mk(self.ao.halo_recv_bytes(1))]
         self.width = camera.pixelWidth
+        if mode == "native" and world > 1:
+            self._connect_native(dev)
+
+    def _connect_native(self, dev) -> None:
+        """Swap the arena handles with every rank (one all_gather of 128 bytes) and map the two neighbours' arenas."""
+        import torch
+        import torch.distributed as dist
+        mine = torch.frombuffer(bytearray(self.ao.band_export()), dtype=torch.uint8)
+        backend = dist.get_backend(self.group)
+        mine = mine.to(dev) if backend == "nccl" else mine
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=self.group)
+        handles = [bytes(h.cpu().numpy().tobytes()) for h in allh]
+        if self.rank > 0:
+            self.ao.band_connect(0, handles[self.rank - 1])
+        if self.rank + 1 < self.world:
+            self.ao.band_connect(1, handles[self.rank + 1])
+        dist.barrier(group=self.group)      # nobody steps before every mapping exists
 
     @property
     def rows(self) -> int:
@@ -81,9 +106,23 @@ class RowTiledAO:
         """depth_band: CUDA f32 [rows, W]; out_band: CUDA u8 [rows, W].  Everything is enqueued on `stream`
         (default: torch's current stream), the P2P included, so steps can be issued back to back."""
         ao = self.ao
+        if self.mode == "native":
+            ao.band_step(depth_band, out_band, stream=stream)                        # ONE graph, exchange kernel inside
+            return
+        import torch
         ao.band_phase_a(depth_band, self.send[0], self.send[1], stream=stream)       # graph: prepare_depth + pack
-        exchange(self.send[0], self.send[1], self.recv[0], self.recv[1], self.rank, self.world)
+        # NCCL enqueues the P2P on torch's CURRENT stream: make `stream` current so pack -> send and recv -> unpack are ordered
+        with torch.cuda.stream(stream) if stream is not None else _null_ctx():
+            exchange(self.send[0], self.send[1], self.recv[0], self.recv[1], self.rank, self.world, self.group)
         ao.band_phase_b(self.recv[0], self.recv[1], out_band, stream=stream)         # graph: unpack + 8 kernels (DAG)
+
+
+class _null_ctx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
 
 
 def halo_slices(rows: list[tuple[int, int]], widths: list[int]) -> list[tuple[int, int, int]]:

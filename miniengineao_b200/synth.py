@@ -73,16 +73,21 @@ def corridor(width: int, height: int, *, frame: int = 0, seed: int = 0xA0, noise
         t = np.minimum(t, np.where(dy < 0, -2.0 / dy, np.inf))
         t = np.minimum(t, np.where(dy > 0, 6.0 / dy, np.inf))
         t = np.minimum(t, np.where(dx != 0, 5.0 / np.abs(dx), np.inf))
-        a = dx * dx + 1.0
+        # the cylinders are vertical, so their ray parameter depends on the COLUMN only: evaluate on one row and broadcast
+        # (the same float64 operations per element as the full-frame form, hence the same bits)
+        dx1 = dx[0]
+        a = dx1 * dx1 + 1.0
+        tcyl = np.full(dx1.shape, np.inf)
         for cxs in (-3.5, 3.5):
             for cz in np.arange(4.0, 60.0, 4.0) - zoff:
                 if cz <= 0.6:
                     continue
-                b = -2.0 * (dx * cxs + cz)
+                b = -2.0 * (dx1 * cxs + cz)
                 c = cxs * cxs + cz * cz - 0.25
                 disc = b * b - 4 * a * c
                 tc = np.where(disc > 0, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), np.inf)
-                t = np.minimum(t, np.where(tc > 0, tc, np.inf))
+                tcyl = np.minimum(tcyl, np.where(tc > 0, tc, np.inf))
+        t = np.minimum(t, tcyl[None, :])
     ys, xs = np.meshgrid(np.arange(row0, row1, dtype=np.uint64), np.arange(width, dtype=np.uint64), indexing="ij")
     h = _pcg_hash(xs + np.uint64(width) * ys, seed + frame * 7919)
     z = t * (1.0 + noise * (h.astype(np.float64) / 4294967296.0 - 0.5))

@@ -218,8 +218,9 @@ def blur_upsample(lo_depth, lo_ao_codes, hi_depth, hi_ao_codes, consts, lo_ao2_c
 
 
 def run(depth, render_consts, upsample_consts, zb, *, reversed_z=True, linear=False, return_all=False,
-        exhaustive=False, high_quality_mask=0, render_consts_wide=None):
-    """Whole pipe (AO.cs:511-531).  render_consts / upsample_consts: dicts per level from the oracle."""
+        exhaustive=False, high_quality_mask=0, render_consts_wide=None, single_scale=False):
+    """Whole pipe (AO.cs:511-531).  render_consts / upsample_consts: dicts per level from the oracle.
+    single_scale (BASELINE.json configs[0]): Downsample + Render level 1 + the final-style Upsample fed Occlusion1."""
     H, W = depth.shape
     dims = level_dims(W, H)
     lin_h, low = prepare_depth(depth, zb, reversed_z, linear)
@@ -228,6 +229,13 @@ def run(depth, render_consts, upsample_consts, zb, *, reversed_z=True, linear=Fa
     else:
         pad12 = F(1e5) if reversed_z else F(F(1) / F(zb[1]))
     occ = [None] * 5
+    if single_scale:
+        sw, sh = dims[3]
+        occ[1] = render_ao(low[1], sw, sh, pad12, render_consts[1], exhaustive)
+        res = blur_upsample(low[1], occ[1], lin_h, None, upsample_consts[1], None)
+        if return_all:
+            return {"linear": lin_h, "low": low, "occ": occ, "comb": [res, None, None, None], "pad12": pad12, "hq": [None] * 5}
+        return res
     for k in range(1, 5):
         sw, sh = dims[k + 2]
         occ[k] = render_ao(low[k], sw, sh, pad12 if k <= 2 else F(0), render_consts[k], exhaustive)

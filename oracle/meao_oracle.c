@@ -23,6 +23,40 @@ static inline float mad(float a, float b, float c) { volatile float p = a * b; r
 static inline float mad(float a, float b, float c) { return fmaf(a, b, c); }
 #endif
 
+/* Shader-side division and reciprocal (`x / y`, `1.0 / y` in the HLSL).  Default: IEEE correctly rounded -- the convention the
+ * CUDA path is held to.  D3D11 only guarantees 1 ULP for both, so two LEGAL alternatives can be built to measure how much
+ * that freedom can move the output (oracle/Makefile):
+ *   MEAO_ORACLE_DIV_MODE 1: x / y := x * (1 / y), the reciprocal correctly rounded (what `mul(x, rcp(y))` hardware does: two roundings);
+ *   MEAO_ORACLE_DIV_MODE 2: quotient and reciprocal truncated (round toward zero) instead of rounded to nearest. */
+#ifndef MEAO_ORACLE_DIV_MODE
+#define MEAO_ORACLE_DIV_MODE 0
+#endif
+static inline float rtz_from_double(double q)
+{
+    float f = (float)q;                                         /* nearest */
+    if (f != f || f == 0.0f || isinf(f)) return f;
+    if (fabs((double)f) > fabs(q)) f = nextafterf(f, 0.0f);     /* step back toward zero */
+    return f;
+}
+static inline float grcp(float y)
+{
+#if MEAO_ORACLE_DIV_MODE == 2
+    return rtz_from_double(1.0 / (double)y);                   /* the double quotient of two floats never ties a float boundary inexactly */
+#else
+    return 1.0f / y;
+#endif
+}
+static inline float gdiv(float x, float y)
+{
+#if MEAO_ORACLE_DIV_MODE == 1
+    volatile float r = 1.0f / y; return x * r;
+#elif MEAO_ORACLE_DIV_MODE == 2
+    return rtz_from_double((double)x / (double)y);
+#else
+    return x / y;
+#endif
+}
+
 /* HLSL saturate: NaN -> 0 */
 static inline float sat(float x) { return x > 0.0f ? (x < 1.0f ? x : 1.0f) : 0.0f; }
 /* HLSL min/max: return the non-NaN operand */
@@ -34,12 +68,27 @@ static inline int iclamp(int x, int lo, int hi) { return x < lo ? lo : (x > hi ?
 /* ------------------------------------------------------------------------------------------
  * storage conversions (formats: AmbientOcclusion.cs:262-273)
  * ---------------------------------------------------------------------------------------- */
+/* Default f32 -> f16 store: round to nearest even, overflow -> inf (the convention the CUDA path is held to).
+ * -DMEAO_ORACLE_F16_RTZ builds the other rounding the D3D spec historically allowed for float16 UAV / RT writes: truncation,
+ * where finite values above 65504 store as 65504 (only a true inf stores inf). */
 uint16_t meao_oracle_f32_to_f16_bits(float x)
 {
     uint32_t u; memcpy(&u, &x, 4);
     uint32_t sign = (u >> 16) & 0x8000u;
     uint32_t absu = u & 0x7fffffffu;
     if (absu > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);           /* NaN */
+#ifdef MEAO_ORACLE_F16_RTZ
+    if (absu == 0x7f800000u) return (uint16_t)(sign | 0x7c00u);          /* inf */
+    if (absu >= 0x477fe000u) return (uint16_t)(sign | 0x7bffu);          /* >= 65504: largest finite half */
+    if (absu < 0x33800000u) return (uint16_t)sign;                       /* < 2^-24: below the smallest subnormal half */
+    {
+        int e = (int)(absu >> 23) - 127;
+        uint32_t m = (absu & 0x7fffffu) | 0x800000u;
+        if (e >= -14) return (uint16_t)(sign | (((uint32_t)(e + 15) << 10) + ((m & 0x7fffffu) >> 13)));
+        int shift = 13 + (-14 - e);
+        return (uint16_t)(sign | (shift > 24 ? 0u : (m >> shift)));
+    }
+#endif
     if (absu >= 0x47800000u) {                                           /* >= 65536 (incl. inf) */
         return (uint16_t)(sign | 0x7c00u);
     }
@@ -255,24 +304,79 @@ void meao_oracle_upsample_constants(const MeaoOracle *o, int lo_level,
  * row-striped thread helper: run fn(ctx, gy0, gy1) over [0, ny) thread-group rows
  * ---------------------------------------------------------------------------------------- */
 typedef void (*stripe_fn)(void *ctx, int gy0, int gy1);
-typedef struct { stripe_fn fn; void *ctx; int gy0, gy1; } stripe_job;
-static void *stripe_main(void *p) { stripe_job *j = (stripe_job *)p; j->fn(j->ctx, j->gy0, j->gy1); return NULL; }
+
+/* A persistent worker pool (the first version created and joined `threads` pthreads for every one of the ten stages of a frame,
+ * which at 128 threads cost about as much as the arithmetic).  Work is handed out in chunks of thread-group rows through an
+ * atomic cursor; rows are independent, so the result does not depend on the thread count or on who runs which chunk. */
+#define POOL_MAX 512
+static struct {
+    pthread_mutex_t region;             /* one parallel region at a time */
+    pthread_mutex_t mu;
+    pthread_cond_t go, done;
+    pthread_t tid[POOL_MAX];
+    int nworkers;                       /* threads created so far */
+    unsigned long generation;
+    int active;                         /* workers taking part in the current region */
+    int running;                        /* workers that have not finished the current region yet */
+    stripe_fn fn; void *ctx; int ny, chunk;
+    volatile int cursor;
+} g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
+             {0}, 0, 0, 0, 0, NULL, NULL, 0, 1, 0 };
+
+static void pool_drain(void)
+{
+    for (;;) {
+        int g0 = __atomic_fetch_add(&g_pool.cursor, g_pool.chunk, __ATOMIC_RELAXED);
+        if (g0 >= g_pool.ny) return;
+        int g1 = g0 + g_pool.chunk; if (g1 > g_pool.ny) g1 = g_pool.ny;
+        g_pool.fn(g_pool.ctx, g0, g1);
+    }
+}
+
+static void *pool_worker(void *arg)
+{
+    const int index = (int)(intptr_t)arg;
+    unsigned long seen = 0;
+    pthread_mutex_lock(&g_pool.mu);
+    for (;;) {
+        while (g_pool.generation == seen) pthread_cond_wait(&g_pool.go, &g_pool.mu);
+        seen = g_pool.generation;
+        if (index >= g_pool.active) continue;
+        pthread_mutex_unlock(&g_pool.mu);
+        pool_drain();
+        pthread_mutex_lock(&g_pool.mu);
+        if (--g_pool.running == 0) pthread_cond_signal(&g_pool.done);
+    }
+    return NULL;
+}
 
 static void run_striped(stripe_fn fn, void *ctx, int ny, int threads)
 {
     if (threads < 1) threads = 1;
     if (threads > ny) threads = ny > 0 ? ny : 1;
+    if (threads > POOL_MAX) threads = POOL_MAX;
     if (threads == 1) { fn(ctx, 0, ny); return; }
-    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
-    stripe_job *jobs = (stripe_job *)malloc(sizeof(stripe_job) * (size_t)threads);
-    for (int t = 0; t < threads; t++) {
-        jobs[t].fn = fn; jobs[t].ctx = ctx;
-        jobs[t].gy0 = (int)((long long)ny * t / threads);
-        jobs[t].gy1 = (int)((long long)ny * (t + 1) / threads);
-        pthread_create(&tid[t], NULL, stripe_main, &jobs[t]);
+    pthread_mutex_lock(&g_pool.region);
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.nworkers < threads - 1) {                 /* the calling thread is worker number `threads` */
+        pthread_attr_t at; pthread_attr_init(&at); pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+        if (pthread_create(&g_pool.tid[g_pool.nworkers], &at, pool_worker, (void *)(intptr_t)g_pool.nworkers) != 0) { pthread_attr_destroy(&at); break; }
+        pthread_attr_destroy(&at);
+        g_pool.nworkers++;
     }
-    for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);
-    free(tid); free(jobs);
+    g_pool.fn = fn; g_pool.ctx = ctx; g_pool.ny = ny;
+    g_pool.chunk = (ny + threads * 4 - 1) / (threads * 4); if (g_pool.chunk < 1) g_pool.chunk = 1;
+    g_pool.cursor = 0;
+    g_pool.active = g_pool.nworkers < threads - 1 ? g_pool.nworkers : threads - 1;
+    g_pool.running = g_pool.active;
+    g_pool.generation++;
+    pthread_cond_broadcast(&g_pool.go);
+    pthread_mutex_unlock(&g_pool.mu);
+    pool_drain();
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.running > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+    pthread_mutex_unlock(&g_pool.mu);
+    pthread_mutex_unlock(&g_pool.region);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -290,7 +394,7 @@ static float ds1_linearize(const ds_ctx *c, int x, int y)
     if (o->depth_is_linear) {
         dist = depth;                                                    /* not in the reference: linear-depth ingest */
     } else {
-        dist = 1.0f / mad(c->zb[0], depth, c->zb[1]);                    /* DS1:40 */
+        dist = grcp(mad(c->zb[0], depth, c->zb[1]));                     /* DS1:40 */
         if (o->camera.reversed_z) { if (depth == 0) dist = 1e5f; }       /* DS1:41-42 */
         else                      { if (depth == 1) dist = 1e5f; }       /* DS1:43-44 */
     }
@@ -479,7 +583,7 @@ static void ren_stripe(void *vc, int r0, int r1)
             /* GroupMemoryBarrierWithGroupSync REN:133 */
             for (int ty = 0; ty < 8; ty++) for (int tx = 0; tx < 8; tx++) {
                 unsigned thisIdx = (unsigned)(tx + ty * REN_TILE_DIM + 4 * REN_TILE_DIM + 4);   /* REN:138 */
-                const float invThisDepth = 1.0f / DS[thisIdx];                                   /* REN:140 */
+                const float invThisDepth = grcp(DS[thisIdx]);                                    /* REN:140 */
                 float ao = ren_accumulate(c, DS, REN_TILE_DIM, 0, thisIdx, invThisDepth);        /* REN:142-169 */
                 int ox = ((gx * 8 + tx) << 2) | (z & 3), oy = ((gy * 8 + ty) << 2) | (z >> 2); /* REN:172 */
                 if (ox < ow && oy < oh)
@@ -521,7 +625,7 @@ static void ren_wide_stripe(void *vc, int gy0, int gy1)
         /* GroupMemoryBarrierWithGroupSync REN:133 */
         for (int ty = 0; ty < 16; ty++) for (int tx = 0; tx < 16; tx++) {
             unsigned thisIdx = (unsigned)(tx + ty * REN_TILE_DIM_WIDE + 8 * REN_TILE_DIM_WIDE + 8);   /* REN:136 */
-            const float invThisDepth = 1.0f / DS[thisIdx];                                             /* REN:140 */
+            const float invThisDepth = grcp(DS[thisIdx]);                                              /* REN:140 */
             float ao = ren_accumulate(c, DS, REN_TILE_DIM_WIDE, 1, thisIdx, invThisDepth);             /* REN:142-169 */
             int ox = gx * 16 + tx, oy = gy * 16 + ty;                                                  /* REN:174 */
             if (ox < sw && oy < sh)
@@ -608,13 +712,13 @@ static inline float ups_bilateral(const ups_ctx *c, float HiDepth, float HiAO,
                                   float la0, float la1, float la2, float la3)
 {
     float t = c->kUpsampleTolerance;
-    float w0 = 9.0f / (fabsf(HiDepth - ld0) + t);
-    float w1 = 3.0f / (fabsf(HiDepth - ld1) + t);
-    float w2 = 1.0f / (fabsf(HiDepth - ld2) + t);
-    float w3 = 3.0f / (fabsf(HiDepth - ld3) + t);
+    float w0 = gdiv(9.0f, fabsf(HiDepth - ld0) + t);
+    float w1 = gdiv(3.0f, fabsf(HiDepth - ld1) + t);
+    float w2 = gdiv(1.0f, fabsf(HiDepth - ld2) + t);
+    float w3 = gdiv(3.0f, fabsf(HiDepth - ld3) + t);
     float TotalWeight = (((w0 + w1) + w2) + w3) + c->NoiseFilterStrength;
     float WeightedSum = mad(la3, w3, mad(la2, w2, mad(la1, w1, la0 * w0))) + c->NoiseFilterStrength;
-    return HiAO * WeightedSum / TotalWeight;
+    return gdiv(HiAO * WeightedSum, TotalWeight);
 }
 
 static inline void ups_store(const ups_ctx *c, int x, int y, float v)
@@ -642,7 +746,7 @@ static void ups_stripe(void *vc, int gy0, int gy1)
             }
             AO1[index] = A.w; AO1[index + 1] = A.z; AO1[index + 16] = A.x; AO1[index + 17] = A.y;   /* UPS:62-65 */
             float4_t D = gather4(c->lo_depth, c->low, c->loh, cx, cy);   /* UPS:67 */
-            DC[index] = 1.0f / D.w; DC[index + 1] = 1.0f / D.z; DC[index + 16] = 1.0f / D.x; DC[index + 17] = 1.0f / D.y;
+            DC[index] = grcp(D.w); DC[index + 1] = grcp(D.z); DC[index + 16] = grcp(D.x); DC[index + 17] = grcp(D.y);
         }
         /* barrier UPS:192 */
         for (int GI = 0; GI < 39; GI++)                                  /* UPS:199-200 */
@@ -676,6 +780,7 @@ void meao_oracle_upsample(MeaoOracle *o, int lo_level, int threads)
     int hi = lo_level - 1;
     c.lo_depth = o->low_depth[lo_level];
     c.lo_ao = (lo_level == 4) ? o->occlusion[4] : o->combined[lo_level];
+    if (o->single_scale && lo_level == 1) c.lo_ao = o->occlusion[1];     /* single-scale: LoResAO1 = Occlusion1, nothing coarser contributes */
     c.lo_ao2 = ((o->high_quality_mask >> (lo_level - 1)) & 1) ? o->high_quality[lo_level] : NULL;   /* kernels main_premin / main_premin_blendout */
     c.hi_depth = (hi == 0) ? o->linear_depth : o->low_depth[hi];
     c.hi_ao = (hi == 0) ? NULL : o->occlusion[hi];
@@ -691,6 +796,14 @@ void meao_oracle_upsample(MeaoOracle *o, int lo_level, int threads)
 void meao_oracle_run(MeaoOracle *o, const float *depth, int threads)
 {
     meao_oracle_downsample(o, depth, threads);
+    if (o->single_scale) {
+        /* BASELINE.json configs[0] "single-scale AO" (SURVEY.md 8d item 1): DS1 + REN level 1 + the final-style UPS only -- three of
+         * the ten dispatches of AO.cs:511-531: :513 (Downsample1; Downsample2 also runs, its outputs are unused), :519 (Render
+         * TiledDepth1 -> Occlusion1) and :531's dispatch (Upsample kernel "main", LinearDepth as HiResDB) fed Occlusion1 as LoResAO1. */
+        meao_oracle_render(o, 1, threads);
+        meao_oracle_upsample(o, 1, threads);
+        return;
+    }
     for (int k = 1; k <= 4; k++) meao_oracle_render(o, k, threads);
     for (int k = 1; k <= 4; k++)                                          /* not in AO.cs: upstream's per-level high-quality pass */
         if ((o->high_quality_mask >> (k - 1)) & 1) meao_oracle_render_wide(o, k, threads);

@@ -26,8 +26,10 @@
  *   - fp32 arithmetic, round-to-nearest-even; a*b+c written in ONE HLSL expression is
  *     contracted to a fused mad (explicit fmaf below; compile with -ffp-contract=off so
  *     nothing else fuses).  Build with -DMEAO_ORACLE_NO_FMA to get the unfused variant.
- *   - x / y and 1 / y are IEEE correctly rounded.
+ *   - x / y and 1 / y are IEEE correctly rounded.  (D3D11 guarantees only 1 ULP: -DMEAO_ORACLE_DIV_MODE=1 builds
+ *     x / y := x * (1 / y), =2 builds truncated quotients, to measure what that freedom can change -- DESIGN.md section 3.)
  *   - f32 -> f16 store: round-to-nearest-even, overflow -> +inf.  f16 -> f32 load: exact.
+ *     (-DMEAO_ORACLE_F16_RTZ builds the truncating store the D3D spec also allowed.)
  *   - f32 -> UNORM8 store: NaN -> 0, clamp to [0,1], k = (uint)(x * 255.0f + 0.5f).
  *     UNORM8 -> f32 load: (float)k * (1.0f / 255.0f).
  *   - out-of-bounds texture Load -> 0; out-of-bounds UAV store -> dropped.
@@ -78,6 +80,8 @@ typedef struct MeaoOracle {
     int high_quality_mask;          /* bit k-1: level k also runs Render.compute kernel "main" (WIDE_SAMPLING, non-tiled source
                                        LowDepth<k>, AO.cs:679) into HighQuality<k>, and the upsample whose LOW level is k runs
                                        main_premin / main_premin_blendout with LoResAO2 = HighQuality<k> (Upsample.compute:23,25,58-60) */
+    int single_scale;               /* BASELINE.json configs[0]: meao_oracle_run = Downsample + Render level 1 + final-style Upsample with
+                                       LoResAO1 = Occlusion1 (three of the ten dispatches of AO.cs:511-531) */
     float *linear_depth;            /* id 1      L0      f16   */
     float *low_depth[5];            /* id 2..5   L1..L4  f32   [1..4] */
     float *tiled_depth[5];          /* id 6..9   L3..L6 x16 slices  f16   [1..4] */

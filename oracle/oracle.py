@@ -30,7 +30,8 @@ class _OracleStruct(C.Structure):
     _fields_ = [("W", C.c_int), ("H", C.c_int), ("lw", C.c_int * 7), ("lh", C.c_int * 7),
                 ("quantize_storage", C.c_int), ("depth_is_linear", C.c_int),
                 ("params", OracleParams), ("camera", OracleCamera),
-                ("sample_exhaustively", C.c_int), ("single_pass_stereo", C.c_int), ("high_quality_mask", C.c_int)]
+                ("sample_exhaustively", C.c_int), ("single_pass_stereo", C.c_int), ("high_quality_mask", C.c_int),
+                ("single_scale", C.c_int)]
     # buffer pointers follow; they are reached through meao_oracle_get_buffer
 
 
@@ -39,20 +40,25 @@ def build(force: bool = False) -> None:
     so = os.path.join(_HERE, "libmeao_oracle.so")
     src = os.path.join(_HERE, "meao_oracle.c")
     hdr = os.path.join(_HERE, "meao_oracle.h")
+    mk = os.path.join(_HERE, "Makefile")
     stale = (not os.path.exists(so)
-             or not os.path.exists(os.path.join(_HERE, "libmeao_oracle_nofma.so"))
-             or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)))
+             or any(not os.path.exists(os.path.join(_HERE, f"libmeao_oracle_{v}.so")) for v in VARIANTS if v != "fma")
+             or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(mk)))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "all"], stdout=subprocess.DEVNULL)
 
 
+# "fma" is THE oracle.  The others restate conventions the reference leaves open (meao_oracle.h) and are used only to measure
+# how often each alternative would flip an output code: unfused mad, truncating f16 stores, x/y as x*(1/y), truncated quotients.
+VARIANTS = ("fma", "nofma", "f16rtz", "divmulrcp", "divrtz")
 _libs: dict[str, C.CDLL] = {}
 
 
 def _lib(variant: str = "fma") -> C.CDLL:
     if variant not in _libs:
         build()
-        name = "libmeao_oracle.so" if variant == "fma" else "libmeao_oracle_nofma.so"
+        assert variant in VARIANTS, variant
+        name = "libmeao_oracle.so" if variant == "fma" else f"libmeao_oracle_{variant}.so"
         lib = C.CDLL(os.path.join(_HERE, name))
         lib.meao_oracle_create.restype = C.POINTER(_OracleStruct)
         lib.meao_oracle_create.argtypes = [C.c_int, C.c_int]
@@ -109,7 +115,8 @@ class Oracle:
                  tan_half_fov_h_: float | None = None, reversed_z: bool = True, threads: int = 1,
                  noise_filter_tolerance: float = 0.0, blur_tolerance: float = -4.6,
                  upsample_tolerance: float = -12.0, thickness_modifier: float = 1.0, intensity: float = 1.0,
-                 sample_exhaustively: bool = False, single_pass_stereo: bool = False, high_quality_mask: int = 0):
+                 sample_exhaustively: bool = False, single_pass_stereo: bool = False, high_quality_mask: int = 0,
+                 single_scale: bool = False):
         self._lib = _lib(variant)
         self._o = self._lib.meao_oracle_create(width, height)
         if not self._o:
@@ -122,6 +129,7 @@ class Oracle:
         s.camera.tan_half_fov_h = tan_half_fov_h(width, height) if tan_half_fov_h_ is None else tan_half_fov_h_
         s.camera.reversed_z = int(reversed_z)
         s.sample_exhaustively, s.single_pass_stereo, s.high_quality_mask = int(sample_exhaustively), int(single_pass_stereo), int(high_quality_mask)
+        s.single_scale = int(single_scale)
         p = s.params
         p.noise_filter_tolerance, p.blur_tolerance, p.upsample_tolerance = noise_filter_tolerance, blur_tolerance, upsample_tolerance
         p.thickness_modifier, p.intensity = thickness_modifier, intensity

@@ -35,7 +35,7 @@ int main(int argc, char **argv)
         if (sum < 0.999999f || sum > 1.000001f) { fprintf(stderr, "weights do not sum to 1: %g\n", sum); return 1; }
         if (meao_algorithmic_bytes(c, 0) != 131613600LL) return fail("algorithmic bytes", c);
         /* ABI v2: the undispatched shader variants are plan inputs like the parameters */
-        MeaoVariants v = {0, 1, 12}, back;
+        MeaoVariants v = {0, 1, 12, 0}, back;
         float rw[28], re[28];
         if (meao_kernels_per_frame(c) != 9 || meao_set_variants(c, &v) != 1 || meao_set_variants(c, &v) != 0) return fail("set_variants", c);
         if (meao_get_variants(c, &back) || back.high_quality_mask != 12 || back.sample_exhaustively != 1) return fail("get_variants", c);

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(os.path.dirname(HERE)), "miniengineao_b200", "csrc")
 LIB = os.path.join(HERE, "libmeao_emu.so")
-KERNELS = ["prepare_depth.cu", "render_ao.cu", "blur_upsample.cu", "debug_view.cu", "composite.cu", "halo.cu"]
+KERNELS = ["prepare_depth.cu", "render_ao.cu", "blur_upsample.cu", "debug_view.cu", "composite.cu", "halo.cu", "band_exchange.cu"]
 FLAGS = ["-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-DMEAO_EMULATE", "-I", HERE, "-Wno-unknown-pragmas", "-Wno-unused-function"]
 
 

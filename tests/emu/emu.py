@@ -36,6 +36,10 @@ def lib(defs: tuple[str, ...] = ()) -> C.CDLL:
         l.emu_band_phase_b.argtypes = [C.c_void_p]
         l.emu_get_buffer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         l.emu_debug_view.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        l.emu_set_render_tile.argtypes = [C.c_void_p, C.c_int]
+        l.emu_set_single_scale.argtypes = [C.c_void_p, C.c_int]
+        l.emu_band_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        l.emu_band_flags.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         l.emu_composite.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]
         l.emu_composite_debug.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]
         _libs[key] = l
@@ -54,7 +58,7 @@ def _aligned(a: np.ndarray) -> np.ndarray:
 class EmulatedFrame:
     """One frame through the host-compiled kernels, planned by a plan-only libmeao context (device = -1)."""
 
-    def __init__(self, plan, *, linear: bool = False, defs: tuple[str, ...] = (), use_tma: bool = True):
+    def __init__(self, plan, *, linear: bool = False, defs: tuple[str, ...] = (), use_tma: bool = True, render_tile: int = -1):
         """plan: miniengineao_b200.AmbientOcclusion(camera, device=-1) with parameters / variants already set.
         use_tma: interior tiles take the kernels' TMA path (emulated box loads) -- what runs on the GPU; False forces the
         gather path everywhere (libmeao's MEAO_DISABLE_TMA=1)."""
@@ -78,6 +82,8 @@ class EmulatedFrame:
             pad12 = 1e5 if rz else float(np.float32(1) / np.float32(zb[1]))
         self._h = self._lib.emu_create(self.W, self.H)
         self._lib.emu_set_tma(self._h, int(use_tma))
+        self._lib.emu_set_render_tile(self._h, int(render_tile))       # -1: the planner's rule; 0 / 1 / 2: force 64x32 / 64x16 / 64x8 tiles
+        self._lib.emu_set_single_scale(self._h, int(getattr(plan, "singleScale", False)))
         self._lib.emu_set_constants(self._h, rc, rcw, uc, zb, pad12, int(not linear), int(rz), int(plan.highQualityMask), int(plan.sampleExhaustively))
 
     def __del__(self):
@@ -116,6 +122,20 @@ class EmulatedFrame:
         buf = _aligned(np.ascontiguousarray(packed, np.float32)) if packed.size else _aligned(np.zeros(1, np.float32))
         assert packed.size * 4 == self.plan.halo_recv_bytes(side)
         self._lib.emu_halo(self._h, (C.c_int * 8)(*[v for lohi in rows for v in lohi]), buf.ctypes.data, 0)
+
+    # ---- native neighbour exchange (band_exchange.cu): peers are other EmulatedFrame objects of the same frame size ---------
+    def exchange(self, up=None, down=None, timeout_polls: int = 1000) -> int:
+        """Runs band_exchange_kernel for this band: pushes its border rows straight into the neighbours' LowDepth buffers and
+        handshakes through the epoch flags.  Returns the sticky error (0 = ok)."""
+        ru = (C.c_int * 8)(*[v for lohi in self.plan.halo_rows(0, True) for v in lohi])
+        rd = (C.c_int * 8)(*[v for lohi in self.plan.halo_rows(1, True) for v in lohi])
+        return int(self._lib.emu_band_exchange(self._h, up._h if up is not None else None, down._h if down is not None else None, ru, rd, timeout_polls))
+
+    def flags(self, set_ready_ack=None) -> dict:
+        out = (C.c_int * 8)()
+        arr = (C.c_int * 4)(*set_ready_ack) if set_ready_ack is not None else None
+        self._lib.emu_band_flags(self._h, arr, out)
+        return {"ready": (out[0], out[1]), "ack": (out[2], out[3]), "epoch": out[4], "done": out[5], "error": out[6], "host_error": out[7]}
 
     def band_phase_b(self) -> np.ndarray:
         """-> the band's rows of the AO texture"""

@@ -31,6 +31,10 @@ struct Emu {
     int use_tma = 1;        // 1: interior tiles take the kernels' TMA path (emulated box loads), 0: every tile gathers
     // row band (meao_set_row_band): rows of level k to PRODUCE, k = 0..4 (meao_band_rows "produce"); default = whole frame
     int band0 = 0, band1 = 0, need_lo[5] = {0, 0, 0, 0, 0}, need_hi[5] = {0, 0, 0, 0, 0};
+    int ren_tile = -1;      // render tile-height variant (index into kRenderTileHs); -1 = the planner's rule (meao_api.cu render_tile_variant)
+    int single_scale = 0;   // MeaoVariants.single_scale
+    BandFlags flags{};      // native neighbour exchange (band_exchange.cu)
+    uint32_t host_error = 0;
 };
 
 // what MeaoCtx::make_map hands to cuTensorMapEncodeTiled
@@ -114,8 +118,14 @@ static void run_render(Emu *e, int k, bool wide)
     for (int i = 0; i < n; i++) { a.inv_thickness[i] = it[idx[i]]; a.neg_front[i] = -(a.inv_thickness[i] - 0.5f); a.weight[i] = e->sample_weight[k][idx[i]]; }
     a.reject_fadeoff = e->reject_fadeoff; a.intensity = e->intensity;
     a.row0 = e->need_lo[k]; a.row1 = e->need_hi[k]; a.wide = wide; a.exhaustive = e->exhaustive;
-    const CUtensorMap map = wide ? make_map(e->low[k], 4, e->lw[k], e->lh[k], e->low_pitch[k], kRenderWideBoxW, kRenderWideBoxH)
-                                 : make_map(e->low[k], 4, e->lw[k], e->lh[k], e->low_pitch[k], kRenderBoxW, kRenderBoxH);
+    int tv = e->ren_tile;
+    if (tv < 0) {           // meao_api.cu render_tile_variant
+        const int rows = a.row1 - (a.row0 & ~3);
+        for (tv = 0; tv < kRenderTileVariants - 1; tv++)
+            if (((e->lw[k] + 63) / 64) * ((rows + kRenderTileHs[tv] - 1) / kRenderTileHs[tv]) >= 2 * 148) break;
+    }
+    a.tile_h = kRenderTileHs[tv];
+    const CUtensorMap map = make_map(e->low[k], 4, e->lw[k], e->lh[k], e->low_pitch[k], wide ? kRenderWideBoxW : kRenderBoxW, render_box_h(a.tile_h, wide));
     launch_render_ao(map, e->use_tma != 0, a, nullptr);
 }
 
@@ -124,7 +134,7 @@ static void run_upsample(Emu *e, int lo)
     const int hi = lo - 1;
     UpsampleArgs a{};
     a.lo_depth = e->low[lo]; a.low = e->lw[lo]; a.loh = e->lh[lo]; a.lo_dpitch = e->low_pitch[lo];
-    a.lo_ao = (lo == 4) ? e->occ[4] : e->comb[lo]; a.lo_apitch = e->occ_pitch[lo];
+    a.lo_ao = (e->single_scale && lo == 1) ? e->occ[1] : (lo == 4) ? e->occ[4] : e->comb[lo]; a.lo_apitch = e->occ_pitch[lo];
     if (hi == 0) { a.hi_depth = e->lin; a.hi_is_half = 1; a.hi_dpitch = e->lin_pitch; a.hi_ao = nullptr; a.out = e->result; a.out_pitch = e->result_pitch; }
     else { a.hi_depth = e->low[hi]; a.hi_is_half = 0; a.hi_dpitch = e->low_pitch[hi]; a.hi_ao = e->occ[hi]; a.hi_apitch = e->occ_pitch[hi]; a.out = e->comb[hi]; a.out_pitch = e->occ_pitch[hi]; }
     a.out_row_origin = 0; a.out_vec_ok = 1;
@@ -156,15 +166,58 @@ int emu_selfcheck_unaligned_tma()
 long long emu_tma_box_loads() { return meao_emu::tma_box_loads; }
 
 void emu_set_tma(void *h, int use_tma) { ((Emu *)h)->use_tma = use_tma; }
+void emu_set_render_tile(void *h, int variant) { ((Emu *)h)->ren_tile = variant; }
+void emu_set_single_scale(void *h, int on) { ((Emu *)h)->single_scale = on; }
 
 // in_format: 0 = f32, 1 = D16 codes, 2 = D24S8 words (PrepareArgs.in_format); depth must be 16-byte aligned
 void emu_run(void *h, const void *depth, int in_format)
 {
     Emu *e = (Emu *)h;
     run_downsample(e, depth, in_format);
+    if (e->single_scale) { run_render(e, 1, false); run_upsample(e, 1); return; }    // record_frame_dag, single_scale branch
     for (int k = 1; k <= 4; k++) run_render(e, k, false);
     for (int k = 1; k <= 4; k++) if ((e->hq_mask >> (k - 1)) & 1) run_render(e, k, true);
     for (int lo = 4; lo >= 1; lo--) run_upsample(e, lo);
+}
+
+// ---- native neighbour exchange: band_exchange_kernel with the segments meao_api.cu's record_exchange builds (whole pitched rows
+// copied to the same position in the neighbour's LowDepth buffers).  up / down: the neighbours' Emu handles (NULL = none);
+// rows_up8 / rows_down8 = meao_halo_rows(side, send = 1).  The fiber emulator runs one grid at a time, so the test presets the
+// flags a concurrently running neighbour would have written (emu_band_flags).  Returns the kernel's sticky error.
+int emu_band_exchange(void *h, void *up, void *down, const int *rows_up8, const int *rows_down8, int timeout_polls)
+{
+    Emu *e = (Emu *)h;
+    Emu *peer[2] = {(Emu *)up, (Emu *)down};
+    const int *rows8[2] = {rows_up8, rows_down8};
+    if (e->flags.epoch == 0) e->flags.epoch = 1;
+    XchgArgs a{}; a.nseg = 0;
+    a.local = &e->flags; a.host_error = &e->host_error;
+    a.timeout_ns = (unsigned long long)timeout_polls * 1000ull;       // the emulated global timer advances 1000 "ns" per read
+    for (int side = 0; side < 2; side++) {
+        if (!peer[side]) continue;
+        if (peer[side]->flags.epoch == 0) peer[side]->flags.epoch = 1;
+        a.peer[side] = &peer[side]->flags;
+        for (int k = 1; k <= 4; k++) {
+            const int lo = rows8[side][2 * (k - 1)], rows = rows8[side][2 * (k - 1) + 1] - lo;
+            if (rows <= 0) continue;
+            XchgSeg &g = a.seg[a.nseg++];
+            g.src = (const uint4 *)(e->low[k] + (size_t)lo * e->low_pitch[k]);
+            g.dst = (uint4 *)(peer[side]->low[k] + (size_t)lo * e->low_pitch[k]);
+            g.n16 = (uint32_t)((size_t)rows * e->low_pitch[k] * sizeof(float) / 16); g.side = side;
+        }
+    }
+    launch_band_exchange(a, nullptr);
+    return (int)e->flags.error;
+}
+// out8 = ready[2], ack[2], epoch, done, error, host_error;  set8 (may be NULL) overwrites ready / ack first
+void emu_band_flags(void *h, const int *set_ready_ack4, int *out8)
+{
+    Emu *e = (Emu *)h;
+    if (set_ready_ack4) { for (int i = 0; i < 2; i++) { e->flags.ready[i] = set_ready_ack4[i]; e->flags.ack[i] = set_ready_ack4[2 + i]; } }
+    if (out8) {
+        out8[0] = e->flags.ready[0]; out8[1] = e->flags.ready[1]; out8[2] = e->flags.ack[0]; out8[3] = e->flags.ack[1];
+        out8[4] = e->flags.epoch; out8[5] = e->flags.done; out8[6] = e->flags.error; out8[7] = e->host_error;
+    }
 }
 
 // ---- row bands: the two phases of meao_band_phase_a / _b around the neighbour exchange ----------------------------------
@@ -207,6 +260,7 @@ void emu_halo(void *h, const int *rows8, float *packed, int pack)
 void emu_band_phase_b(void *h)
 {
     Emu *e = (Emu *)h;
+    if (e->single_scale) { run_render(e, 1, false); run_upsample(e, 1); return; }
     for (int k = 1; k <= 4; k++) run_render(e, k, false);
     for (int k = 1; k <= 4; k++) if ((e->hq_mask >> (k - 1)) & 1) run_render(e, k, true);
     for (int lo = 4; lo >= 1; lo--) run_upsample(e, lo);

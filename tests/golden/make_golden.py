@@ -28,6 +28,9 @@ CASES = {
     "variant_hq15_exhaustive_118x90": (118, 90, lambda: synth.random_depth(118, 90, seed=6),
                                        dict(intensity=1.2, thickness_modifier=2.0, high_quality_mask=15, sample_exhaustively=True)),
     "variant_hq10_corridor_144x80": (144, 80, lambda: synth.corridor(144, 80), dict(high_quality_mask=0b1010)),
+    # BASELINE.json configs[0]: 256 x 256 flat + sphere, SINGLE-SCALE plan (Downsample -> Render level 1 -> final-style Upsample);
+    # "variants" then carries a 4th entry = single_scale, and only the buffers that plan writes are stored
+    "single_scale_flat_sphere_256": (256, 256, lambda: synth.flat_sphere(256, 256), dict(intensity=1.1, single_scale=True)),
 }
 
 
@@ -44,9 +47,13 @@ def main():
                                                               kw.get("upsample_tolerance", -12.0), kw.get("thickness_modifier", 1.0),
                                                               kw.get("intensity", 1.0)], np.float32)}
         mask = kw.get("high_quality_mask", 0)
-        if mask or kw.get("sample_exhaustively"):
+        single = bool(kw.get("single_scale", False))
+        if single:
+            data["variants"] = np.array([0, int(kw.get("sample_exhaustively", False)), mask, 1], np.int32)
+        elif mask or kw.get("sample_exhaustively"):
             data["variants"] = np.array([0, int(kw.get("sample_exhaustively", False)), mask], np.int32)
-        for bid in list(range(1, 18)) + [17 + k for k in range(1, 5) if (mask >> (k - 1)) & 1]:
+        bids = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 17] if single else list(range(1, 18)) + [17 + k for k in range(1, 5) if (mask >> (k - 1)) & 1]
+        for bid in bids:
             b = o.buffer(bid)
             if bid >= 10:
                 data[f"buf{bid}"] = o.codes(bid)

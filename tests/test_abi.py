@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (meao_[a-z0-9_]+)", out))
     assert set(decl) <= exported
-    assert lib.meao_abi_version() == 2
+    assert lib.meao_abi_version() == 3
 
 
 def test_library_has_no_driver_link_dependency():
@@ -235,7 +235,7 @@ def test_csharp_host_binds_only_declared_entry_points():
         n_cs = 0 if not args.strip() else args.count(",") + 1
         assert n_c == n_cs, f"{name}: {n_cs} parameters in C#, {n_c} in meao.h"
     # struct mirrors: field counts of the [StructLayout(Sequential)] twins
-    for struct, n in (("MeaoParams", 7), ("MeaoCamera", 4), ("MeaoDeviceCfg", 2), ("MeaoVariants", 3)):
+    for struct, n in (("MeaoParams", 7), ("MeaoCamera", 4), ("MeaoDeviceCfg", 2), ("MeaoVariants", 4)):
         body = re.search(r"public struct " + struct + r"\s*\{(.*?)\}", cs, flags=re.S).group(1)
         fields = sum(len(d.split(",")) for d in re.findall(r"public\s+(?:float|int|uint)\s+([^;]+);", body))
         assert fields == n, (struct, fields)
@@ -251,3 +251,65 @@ def test_csharp_scalar_twin_names_every_oracle_stage():
     for method in ("Downsample", "Render", "Upsample", "Run", "TimeFrames", "Unorm8Code", "SampleThickness"):
         assert re.search(r"\b" + method + r"\s*\(", cs), method
     assert "(GI & 9) == 0" in cs            # Downsample1.compute:73 uses the OCTAL literal 011
+
+
+# ---- round 2: ABI 3 -----------------------------------------------------------------------------------------------------------
+def test_single_scale_variant_is_a_plan_input():
+    ao = AmbientOcclusion(Camera(640, 360), device=-1)
+    ao.LateUpdate()
+    assert ao.kernels_per_frame == 9
+    ao.singleScale = True
+    assert ao.LateUpdate() is True and ao.kernels_per_frame == 3
+    assert ao.LateUpdate() is False
+    v = N.MeaoVariants()
+    N.lib().meao_get_variants(ao._ctx, C.byref(v))
+    assert v.single_scale == 1
+    bad = N.MeaoVariants(0, 0, 3, 1)                     # single_scale excludes the high-quality passes
+    assert N.lib().meao_set_variants(ao._ctx, C.byref(bad)) == N.MEAO_ERR_INVALID
+
+
+def test_refused_row_band_leaves_the_context_untouched():
+    """meao_set_row_band used to commit the band before validating the halo depth."""
+    a = AmbientOcclusion(Camera(1920, 1088), device=-1)
+    a.set_row_band(0, 544, -1, 1088)
+    before = a.band_rows()
+    with pytest.raises(MeaoError) as e:
+        a.set_row_band(272, 544, 0, 816)                 # too thin for the level-4 halo
+    assert e.value.code == N.MEAO_ERR_UNSUPPORTED
+    assert a.band_rows() == before and a._band == (0, 544)
+    assert a.halo_bytes(1) > 0 and a.halo_bytes(0) == 0
+
+
+def test_resize_resets_band_in_the_host_mirror():
+    cam = Camera(640, 720)
+    a = AmbientOcclusion(cam, device=-1)
+    a.set_row_band(0, 368, -1, 720)
+    assert a._band_rows() == 368
+    cam.pixelHeight = 360
+    a.LateUpdate()
+    assert a._band is None and a._band_rows() == 360 and a.band_rows()["produce"][0] == (0, 360)
+
+
+def test_native_exchange_entry_points_need_a_device():
+    a = AmbientOcclusion(Camera(640, 720), device=-1)
+    a.set_row_band(0, 368, -1, 720)
+    with pytest.raises(MeaoError) as e:
+        a.band_export()
+    assert e.value.code == N.MEAO_ERR_CUDA
+    h = N.MeaoPeerHandle()
+    assert N.lib().meao_band_connect(a._ctx, 1, C.byref(h)) == N.MEAO_ERR_CUDA
+    assert N.lib().meao_band_step(a._ctx, None, 0, None, None) == N.MEAO_ERR_CUDA
+    st = (C.c_int32 * 4)()
+    assert N.lib().meao_band_status(a._ctx, st) == N.MEAO_ERR_INVALID
+    assert C.sizeof(N.MeaoPeerHandle) == N.MEAO_PEER_HANDLE_BYTES == 128
+    assert a.pdl_level == -1
+
+
+def test_bad_depth_kind_is_refused_by_every_entry_point():
+    """only meao_render validated depth_kind; the check now sits in the downsample recorder (shared by all entry
+    points).  Without a device the calls fail earlier with MEAO_ERR_CUDA, so this checks the declared contract in the header."""
+    hdr = open(os.path.join(ROOT, "include", "meao.h")).read()
+    assert "MEAO_DEPTH_RAW_D24S8 = 3" in hdr
+    src = open(os.path.join(ROOT, "miniengineao_b200", "csrc", "meao_api.cu")).read()
+    rec = src[src.index("int record_downsample("):]
+    assert "bad depth kind" in rec[:600]

@@ -182,3 +182,105 @@ def test_build_switches_keep_the_arithmetic(defs):
     depth = synth.lin01_to_raw(synth.random_depth(120, 80, seed=2))
     depth[10:30, 15:60] = 0.0
     _run(120, 80, depth=depth, defs=defs, high_quality_mask=15)
+
+
+# ---- round 2: render tile-height variants, single-scale plan, native neighbour exchange ---------------------------------------
+@pytest.mark.parametrize("tile", [0, 1, 2])
+@pytest.mark.parametrize("use_tma", [True, False])
+def test_render_tile_height_variants(tile, use_tma):
+    """render_ao_kernel<MODE, EXH, TH> for TH = 32 / 16 / 8 (kernels.h kRenderTileHs): the coarse levels take the small tiles on the
+    GPU (meao_api.cu render_tile_variant); every variant must give the same bits on interior (TMA) and border (gather) tiles."""
+    W, H = 700, 420
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=31))
+    depth[100:140, 200:330] = 0.0
+    orc = Oracle(W, H, threads=4, intensity=1.1, high_quality_mask=0b0011)
+    ref = orc.run(depth)
+    f = EmulatedFrame(_plan(W, H, intensity=1.1, high_quality_mask=0b0011), use_tma=use_tma, render_tile=tile)
+    n0 = f.tma_box_loads()
+    assert np.array_equal(f.run(depth), ref)
+    _compare_all(f, orc, f"tile variant {tile}", 0b0011)
+    assert (f.tma_box_loads() - n0 > 50) if use_tma else (f.tma_box_loads() == n0)
+
+
+@pytest.mark.parametrize("W,H", [(256, 256), (130, 70), (321, 203), (3, 5)])
+def test_single_scale_plan(W, H):
+    """BASELINE.json configs[0]: Downsample -> Render level 1 -> final-style Upsample on Occlusion1 (MeaoVariants.single_scale)."""
+    lin = synth.flat_sphere(W, H) if (W, H) == (256, 256) else synth.random_depth(W, H, seed=W)
+    depth = synth.lin01_to_raw(lin)
+    orc = Oracle(W, H, threads=4, intensity=1.1, single_scale=True)
+    ref = orc.run(depth)
+    plan = _plan(W, H, intensity=1.1)
+    plan.singleScale = True
+    f = EmulatedFrame(plan)
+    assert np.array_equal(f.run(depth), ref)
+    for bid in (1, 2, 3, 4, 5, 10, 17):
+        got = f.buffer(bid)
+        want = orc.codes(bid) if got.dtype == np.uint8 else orc.buffer(bid)
+        with np.errstate(over="ignore"):
+            assert np.array_equal(got, want.astype(got.dtype)), bid
+    assert plan.kernels_per_frame == 3
+
+
+def _band_frames(W, H, nb, **kw):
+    from miniengineao_b200 import rowtile
+    cuts = rowtile.partition(H, nb)
+    frames = []
+    for i in range(nb):
+        plan = _plan(W, H, **kw)
+        plan.set_row_band(cuts[i], cuts[i + 1], *rowtile.neighbours(cuts, i))
+        f = EmulatedFrame(plan)
+        f.use_plan_band()
+        frames.append(f)
+    return cuts, frames
+
+
+@pytest.mark.parametrize("W,H,nb", [(200, 528, 2), (130, 1296, 3)])
+def test_native_exchange_kernel_bands_equal_whole_frame(W, H, nb):
+    """band_exchange_kernel (peer stores + epoch flags): each band pushes its border rows of LowDepth1..4 straight into the
+    neighbours' buffers (NaN-poisoned beforehand); the union of the bands must equal the whole-frame oracle bit for bit.
+    The fiber emulator runs one grid at a time, so the flags a CONCURRENT neighbour would have raised are preset for the band
+    that runs first; every later band finds them raised by the kernels that already ran."""
+    depth = synth.lin01_to_raw(synth.random_depth(W, H, seed=3))
+    ref = Oracle(W, H, threads=4, intensity=1.1).run(depth)
+    for frame_no in (1, 2):                                      # two epochs through the same flags
+        cuts, frames = (_band_frames(W, H, nb, intensity=1.1)) if frame_no == 1 else (cuts, frames)
+        d = depth if frame_no == 1 else depth[:, ::-1].copy()
+        want = ref if frame_no == 1 else Oracle(W, H, threads=4, intensity=1.1).run(d)
+        for i, f in enumerate(frames):
+            if frame_no == 2:
+                f._lib.emu_poison_low(f._h)
+        for i, f in enumerate(frames):
+            f.band_phase_a(d[cuts[i]:cuts[i + 1]])
+        for i, f in enumerate(frames):
+            up = frames[i - 1] if i > 0 else None
+            down = frames[i + 1] if i + 1 < nb else None
+            fl = f.flags()
+            # what the not-yet-run neighbour below WOULD have written by now: its announce (ack) and its rows (ready)
+            f.flags(set_ready_ack=(fl["ready"][0], frame_no if down is not None else 0, fl["ack"][0], frame_no if down is not None else 0))
+            assert f.exchange(up, down) == 0
+            after = f.flags()
+            assert after["epoch"] == frame_no + 1 and after["done"] == 0 and after["error"] == 0 and after["host_error"] == 0
+        for i, f in enumerate(frames):
+            if i + 1 < nb:                                       # the rows really came from the neighbour, not from the preset flags
+                assert frames[i + 1].flags()["ready"][0] == frame_no and frames[i + 1].flags()["ack"][0] == frame_no
+            got = f.band_phase_b()
+            assert np.array_equal(got, want[cuts[i]:cuts[i + 1]]), (frame_no, i)
+
+
+def test_native_exchange_times_out_instead_of_hanging():
+    """A neighbour that never arrives: the kernel gives up after the time-out, sets the sticky error (1 = no ack, 2 = no rows),
+    mirrors it to the host word, and later exchanges return immediately."""
+    cuts, frames = _band_frames(200, 528, 2, intensity=1.1)
+    depth = synth.lin01_to_raw(synth.random_depth(200, 528, seed=3))
+    a, b = frames
+    a.band_phase_a(depth[cuts[0]:cuts[1]])
+    assert a.exchange(None, b, timeout_polls=50) == 1            # b never announced: no ack
+    st = a.flags()
+    assert st["error"] == 1 and st["host_error"] == 1 and st["epoch"] == 2 and st["done"] == 0
+    # nothing was written into the neighbour (its LowDepth rows are still poisoned), but it was told we are at epoch 1
+    assert b.flags()["ack"][0] == 1 and b.flags()["ready"][0] == 1
+    assert np.isnan(b.buffer(2)).all()
+    b.band_phase_a(depth[cuts[1]:cuts[2]])
+    b.flags(set_ready_ack=(0, 0, 1, 0))                          # ack from a, but a's rows "never arrive"
+    assert b.exchange(a, None, timeout_polls=50) == 2
+    assert b.flags()["host_error"] == 2

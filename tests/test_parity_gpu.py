@@ -6,6 +6,8 @@ so any differing code would already be out of tolerance (TOL_CODES = 0).
 The reference publishes no golden vectors (parity unpinned, see oracle/meao_oracle.h); the oracle
 is pinned by analytic identities and a second independent restatement in tests/test_oracle.py.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -17,7 +19,8 @@ TOL_CODES = 0   # allowed |delta| in unorm8 codes; 1e-3 absolute < 1/255
 @pytest.fixture(scope="module")
 def torch_cuda():
     import torch
-    assert torch.cuda.is_available(), "GPU tests need a GPU"
+    if not torch.cuda.is_available():
+        pytest.skip("GPU tests need a GPU")
     return torch
 
 
@@ -282,10 +285,16 @@ def test_host_buffer_path_and_event_hook(torch_cuda):
     d = torch.from_numpy(depth).cuda()
     out = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
     lib = N.lib()
-    N.check(ao._ctx, lib.meao_bind_event(ao._ctx, 42, d.data_ptr(), 0, out.data_ptr()))
+    st = torch.cuda.Stream()                                   # ABI 3: the event renders on the stream it was bound with
+    N.check(ao._ctx, lib.meao_bind_event(ao._ctx, 42, d.data_ptr(), 0, out.data_ptr(), st.cuda_stream))
     fn = lib.meao_get_render_event_func()
     fn(42)
-    ao.synchronize()
+    st.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    out.zero_()
+    N.check(ao._ctx, lib.meao_bind_event(ao._ctx, 43, d.data_ptr(), 0, out.data_ptr(), None))     # NULL = legacy default stream
+    fn(43)
+    torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), ref)
 
 
@@ -725,10 +734,12 @@ def test_cuda_reproduces_golden_fixture(torch_cuda, path):
     torch = torch_cuda
     g = np.load(path)
     H, W = g["depth"].shape
-    v = g["variants"] if "variants" in g.files else np.zeros(3, np.int32)
+    v = np.zeros(4, np.int32)
+    if "variants" in g.files:
+        v[:len(g["variants"])] = g["variants"]
     ao = AmbientOcclusion(Camera(W, H), device=0)
     (ao.noiseFilterTolerance, ao.blurTolerance, ao.upsampleTolerance, ao.thicknessModifier, ao.intensity) = (float(x) for x in g["params"])
-    ao.sampleExhaustively, ao.highQualityMask = bool(v[1]), int(v[2])
+    ao.sampleExhaustively, ao.highQualityMask, ao.singleScale = bool(v[1]), int(v[2]), bool(v[3])
     got = ao.render(torch.from_numpy(g["depth"]).cuda()).cpu().numpy()
     assert np.array_equal(got, g["ao"]), os.path.basename(path)
     for key in g.files:
@@ -762,3 +773,203 @@ def test_debug_composite_replaces_the_camera_target(torch_cuda):
             assert np.array_equal(target.cpu().numpy().view(np.uint8), O.composite_debug(view, like).view(np.uint8)), (dbg, like.dtype)
     ao.debug = 0
     assert np.array_equal(ao.render(torch.from_numpy(depth).cuda()).cpu().numpy(), ref_ao)       # the debug property re-plans, nothing else
+
+
+# ---- round 2 --------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("W,H", [(256, 256), (130, 70), (1920, 1080)])
+def test_single_scale_plan_bit_exact(torch_cuda, W, H):
+    """BASELINE.json configs[0]: Downsample -> Render level 1 -> final-style Upsample on Occlusion1 (3 kernels), vs the oracle's twin."""
+    from miniengineao_b200 import AmbientOcclusion, Camera, synth
+    from oracle.oracle import Oracle
+    torch = torch_cuda
+    lin = synth.flat_sphere(W, H) if (W, H) == (256, 256) else (synth.corridor(W, H) if W > 1000 else synth.random_depth(W, H, seed=2))
+    depth = synth.lin01_to_raw(lin)
+    orc = Oracle(W, H, threads=8, intensity=1.1, single_scale=True)
+    ref = orc.run(depth)
+    ao = AmbientOcclusion(Camera(W, H), device=0)
+    ao.intensity, ao.singleScale = 1.1, True
+    n0 = ao.launch_count
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert ao.kernels_per_frame == 3 and ao.launch_count - n0 == 3
+    assert np.array_equal(ao.debug_buffer(10), orc.codes(10))
+    assert np.array_equal(ao.render_host(depth), ref)
+    ao.singleScale = False                                  # back to the reference plan: re-plans, 9 kernels, the multi-scale answer
+    full = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert np.array_equal(full, Oracle(W, H, threads=8, intensity=1.1).run(depth)) and ao.kernels_per_frame == 9
+
+
+@pytest.mark.parametrize("tile", ["0", "1", "2"])
+def test_render_tile_variants_forced(torch_cuda, tile, monkeypatch):
+    """render_ao_kernel<.., TH> for TH = 32 / 16 / 8 forced on EVERY level (MEAO_REN_TILE), TMA and gather tiles, all buffers."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    monkeypatch.setenv("MEAO_REN_TILE", tile)
+    W, H = 1920, 1080
+    ao, orc = _mk(W, H, intensity=1.1, high_quality_mask=0b0101)
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    ref = orc.run(depth)
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()
+    assert np.array_equal(got, ref)
+    _compare_all(ao, orc, f"MEAO_REN_TILE={tile}", extra=[18, 20])
+
+
+def _native_bands(torch, W, H, bands, device=0, **attrs):
+    """`bands` band contexts on ONE device, connected to each other through meao_band_export / meao_band_connect (in-process:
+    direct pointers) -- the same kernels, flags and graph as across GPUs, minus NVLink."""
+    from miniengineao_b200 import AmbientOcclusion, Camera, rowtile
+    cuts = rowtile.partition(H, bands)
+    ctxs = []
+    for i in range(bands):
+        a = AmbientOcclusion(Camera(W, H), device=device)
+        for k, v in attrs.items():
+            setattr(a, k, v)
+        a.set_row_band(cuts[i], cuts[i + 1], *rowtile.neighbours(cuts, i))
+        ctxs.append(a)
+    handles = [a.band_export() for a in ctxs]
+    for i, a in enumerate(ctxs):
+        if i > 0:
+            a.band_connect(0, handles[i - 1])
+        if i + 1 < bands:
+            a.band_connect(1, handles[i + 1])
+    streams = [torch.cuda.Stream() for _ in range(bands)]      # one stream per band, like one GPU per band: the exchange kernels must overlap
+    return cuts, ctxs, streams
+
+
+@pytest.mark.parametrize("W,H,bands", [(1920, 1080, 2), (3840, 2160, 4), (2560, 1440, 3)])
+def test_native_exchange_bands_equal_oracle(torch_cuda, W, H, bands):
+    """meao_band_step: ONE graph per band (prepare_depth -> band_exchange_kernel -> render x4 + upsample x4); the halo rows move by
+    peer stores + epoch flags inside the graph.  Three frames with different depth through the same graphs / flags; the union of
+    the bands must equal the ORACLE's whole frame bit for bit every time."""
+    from miniengineao_b200 import synth
+    from oracle.oracle import Oracle
+    torch = torch_cuda
+    cuts, ctxs, streams = _native_bands(torch, W, H, bands, intensity=1.1)
+    outs = [torch.zeros((cuts[i + 1] - cuts[i], W), dtype=torch.uint8, device="cuda") for i in range(bands)]
+    bufs = [torch.empty((cuts[i + 1] - cuts[i], W), dtype=torch.float32, device="cuda") for i in range(bands)]
+    orc = Oracle(W, H, threads=8, intensity=1.1)
+    for frame in range(3):
+        depth = synth.lin01_to_raw(synth.corridor(W, H, frame=frame) if frame < 2 else synth.random_depth(W, H, seed=9))
+        ref = orc.run(depth)
+        for i in range(bands):
+            bufs[i].copy_(torch.from_numpy(depth[cuts[i]:cuts[i + 1]]))
+            outs[i].zero_()
+        torch.cuda.synchronize()
+        for i, a in enumerate(ctxs):                            # issue order is irrelevant: the kernels handshake on the device
+            a.band_step(bufs[i], outs[i], stream=streams[i])
+        torch.cuda.synchronize()
+        got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+        assert int((got != ref).sum()) == 0, frame
+        for a in ctxs:
+            st = a.band_status()
+            assert st["error"] == 0 and st["epoch"] == frame + 2, st
+    assert ctxs[0].launch_count == 3 * 10 and ctxs[1].launch_count == 3 * 10
+
+
+def test_native_exchange_8k_bands_equal_oracle(torch_cuda):
+    """BASELINE.json configs[3] at full size against the ORACLE (not against our own single-GPU frame): 7680 x 4320, 8 bands."""
+    from miniengineao_b200 import synth
+    from oracle.oracle import Oracle
+    torch = torch_cuda
+    W, H, bands = 7680, 4320, 8
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    ref = Oracle(W, H, threads=os.cpu_count() or 8, intensity=1.1).run(depth)
+    cuts, ctxs, streams = _native_bands(torch, W, H, bands, intensity=1.1)
+    outs = [torch.zeros((cuts[i + 1] - cuts[i], W), dtype=torch.uint8, device="cuda") for i in range(bands)]
+    bufs = [torch.from_numpy(depth[cuts[i]:cuts[i + 1]]).cuda() for i in range(bands)]
+    for rep in range(2):
+        for i, a in enumerate(ctxs):
+            a.band_step(bufs[i], outs[i], stream=streams[i])
+        torch.cuda.synchronize()
+        got = np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+        assert int((got != ref).sum()) == 0, rep
+    del ctxs
+
+
+def test_native_exchange_missing_neighbour_times_out(torch_cuda, monkeypatch):
+    """A band whose neighbour never steps: the exchange kernel gives up after MEAO_BAND_TIMEOUT_MS, the step completes (on stale
+    halo rows), the sticky error is visible in meao_band_status and the NEXT meao_band_step is refused with MEAO_ERR_PEER."""
+    import time
+    from miniengineao_b200 import MeaoError, synth
+    from miniengineao_b200 import _native as N
+    torch = torch_cuda
+    monkeypatch.setenv("MEAO_BAND_TIMEOUT_MS", "100")
+    W, H = 1280, 720
+    cuts, ctxs, streams = _native_bands(torch, W, H, 2, intensity=1.1)
+    depth = torch.from_numpy(synth.lin01_to_raw(synth.corridor(W, H))).cuda()
+    out = torch.zeros((cuts[1], W), dtype=torch.uint8, device="cuda")
+    t0 = time.time()
+    ctxs[0].band_step(depth[:cuts[1]].contiguous(), out, stream=streams[0])
+    torch.cuda.synchronize()
+    assert 0.09 < time.time() - t0 < 5.0
+    st = ctxs[0].band_status()
+    assert st["error"] == 1 and st["epoch"] == 2, st
+    with pytest.raises(MeaoError) as e:
+        ctxs[0].band_step(depth[:cuts[1]].contiguous(), out, stream=streams[0])
+    assert e.value.code == N.MEAO_ERR_PEER
+    # an unconnected interior band is refused up front
+    from miniengineao_b200 import AmbientOcclusion, Camera, rowtile
+    lone = AmbientOcclusion(Camera(W, H), device=0)
+    lone.set_row_band(cuts[0], cuts[1], *rowtile.neighbours(cuts, 0))
+    with pytest.raises(MeaoError) as e2:
+        lone.band_step(depth[:cuts[1]].contiguous(), out)
+    assert e2.value.code == N.MEAO_ERR_INVALID
+
+
+def test_resize_after_row_band_resets_the_band(torch_cuda):
+    """meao_resize re-allocates and falls back to the whole frame; the host mirror must follow (it used to keep the old
+    band height and hand band-sized tensors to a whole-frame context)."""
+    from miniengineao_b200 import AmbientOcclusion, Camera, synth
+    from oracle.oracle import Oracle
+    torch = torch_cuda
+    cam = Camera(640, 720)
+    ao = AmbientOcclusion(cam, device=0)
+    ao.set_row_band(0, 368, -1, 720)
+    assert ao._band_rows() == 368
+    cam.pixelHeight = 360                                        # camera size change
+    depth = synth.lin01_to_raw(synth.random_depth(640, 360, seed=1))
+    got = ao.render(torch.from_numpy(depth).cuda()).cpu().numpy()       # whole 640 x 360 frame: shapes are checked against the new size
+    assert ao._band_rows() == 360 and got.shape == (360, 640)
+    assert np.array_equal(got, Oracle(640, 360, threads=4).run(depth))
+    assert ao.band_rows()["produce"][0] == (0, 360)
+
+
+def test_graph_cache_retargets_instead_of_flushing(torch_cuda):
+    """More distinct (depth, out) pairs than the 64-entry graph cache: the least recently used executable graph is re-targeted with
+    cudaGraphExecUpdate (no device-wide synchronise + destroy-all), results stay exact and frames in flight are unaffected."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 320, 200
+    ao, orc = _mk(W, H, intensity=1.1)
+    depths, refs = [], []
+    for i in range(3):
+        d = synth.lin01_to_raw(synth.random_depth(W, H, seed=20 + i))
+        depths.append(torch.from_numpy(d).cuda()); refs.append(orc.run(d).copy())
+    outs = [torch.zeros((H, W), dtype=torch.uint8, device="cuda") for _ in range(80)]
+    for rnd in range(2):
+        for i, o in enumerate(outs):                             # 80 output buffers x 3 depth buffers = 240 keys
+            ao.render(depths[i % 3], o)
+        torch.cuda.synchronize()
+        for i, o in enumerate(outs):
+            assert np.array_equal(o.cpu().numpy(), refs[i % 3]), (rnd, i)
+            o.zero_()
+
+
+def test_pdl_level_is_reported_and_results_do_not_depend_on_it(torch_cuda, monkeypatch):
+    """Programmatic dependent launch inside the captured graph (MEAO_PDL caps the level): same bits with and without."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    W, H = 1920, 1080
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    d = torch.from_numpy(depth).cuda()
+    results = []
+    for lvl in ("0", "1", "2"):
+        monkeypatch.setenv("MEAO_PDL", lvl)
+        ao, orc = _mk(W, H, intensity=1.1)
+        a = ao.render(d).cpu().numpy()
+        b = ao.render(d).cpu().numpy()                           # replay of the cached graph
+        assert np.array_equal(a, b)
+        results.append(a)
+        assert 0 <= ao.pdl_level <= int(lvl)
+    assert np.array_equal(results[0], results[1]) and np.array_equal(results[0], results[2])
+    assert np.array_equal(results[0], orc.run(depth))
