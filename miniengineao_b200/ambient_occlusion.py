@@ -199,19 +199,19 @@ class AmbientOcclusion:
         return out
 
     def render_host_batch(self, depths, outs, *, linear: bool = False) -> None:
-        """Frame stream with HOST buffers: depths[i] (float32 [H, W]) -> outs[i] (uint8 [H, W]).  Frames alternate
+        """Frame stream with HOST buffers: depths[i] (float32, or uint16 D16_UNORM codes, [H, W]) -> outs[i] (uint8 [H, W]).  Frames alternate
         over the two staging slots of the context, so the H2D copy of frame i+1 overlaps the kernels and the D2H
         copy of frame i.  Pass pinned arrays (meao_host_alloc) for real overlap; the arrays must stay alive and
         untouched until this call returns."""
         self.LateUpdate()
         rows = self._band_rows()
-        kind = N.MEAO_DEPTH_LINEAR_F32 if linear else N.MEAO_DEPTH_RAW_F32
         n = len(depths)
         assert len(outs) == n
         for i in range(n):
             d, o = depths[i], outs[i]
-            if d.dtype != np.float32 or not d.flags.c_contiguous or d.shape != (rows, self._width):
-                raise ValueError("depths[i] must be C-contiguous float32 [rows, W]")
+            if d.dtype not in (np.float32, np.uint16) or not d.flags.c_contiguous or d.shape != (rows, self._width):
+                raise ValueError("depths[i] must be C-contiguous float32 (or uint16 D16 codes) [rows, W]")
+            kind = self._kind(d.dtype.name, linear)
             if o.dtype != np.uint8 or not o.flags.c_contiguous or o.shape != (rows, self._width):
                 raise ValueError("outs[i] must be C-contiguous uint8 [rows, W]")
             slot = i & 1

@@ -59,6 +59,9 @@ def flat_sphere(width: int = 256, height: int = 256, *, plane_z: float = 10.0, s
     return (z / far).astype(np.float32)
 
 
+_corridor_cache: dict = {}
+
+
 def corridor(width: int, height: int, *, frame: int = 0, seed: int = 0xA0, noise: float = 1e-4,
              row0: int = 0, row1: int | None = None, far: float = FAR) -> np.ndarray:
     """lin01 of the "Sponza-like" corridor: floor y=-2, ceiling y=+6, walls x=+-5, end wall z=60, two rows
@@ -66,16 +69,22 @@ def corridor(width: int, height: int, *, frame: int = 0, seed: int = 0xA0, noise
     noise so that no two neighbouring depths tie exactly.  Closed box: no sky pixels.
     Rows [row0,row1) only (bands of a large frame can be generated independently)."""
     row1 = height if row1 is None else row1
-    dx, dy = _pixel_rays(width, height, row0, row1)
     zoff = 0.25 * frame
+    key = (width, height, row0, row1)
+    if _corridor_cache.get("key") != key:       # floor / ceiling / side walls do not depend on the frame index: kept for frame streams
+        dx, dy = _pixel_rays(width, height, row0, row1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            planes = np.where(dy < 0, -2.0 / dy, np.inf)
+            planes = np.minimum(planes, np.where(dy > 0, 6.0 / dy, np.inf))
+            planes = np.minimum(planes, np.where(dx != 0, 5.0 / np.abs(dx), np.inf))
+        ys, xs = np.meshgrid(np.arange(row0, row1, dtype=np.uint64), np.arange(width, dtype=np.uint64), indexing="ij")
+        _corridor_cache.clear()
+        _corridor_cache.update(key=key, dx1=dx[0].copy(), planes=planes, idx=xs + np.uint64(width) * ys)
+    dx1, planes, idx = _corridor_cache["dx1"], _corridor_cache["planes"], _corridor_cache["idx"]
     with np.errstate(divide="ignore", invalid="ignore"):
-        t = np.full(dx.shape, 60.0 - zoff)
-        t = np.minimum(t, np.where(dy < 0, -2.0 / dy, np.inf))
-        t = np.minimum(t, np.where(dy > 0, 6.0 / dy, np.inf))
-        t = np.minimum(t, np.where(dx != 0, 5.0 / np.abs(dx), np.inf))
+        t = np.minimum(planes, 60.0 - zoff)     # end wall
         # the cylinders are vertical, so their ray parameter depends on the COLUMN only: evaluate on one row and broadcast
         # (the same float64 operations per element as the full-frame form, hence the same bits)
-        dx1 = dx[0]
         a = dx1 * dx1 + 1.0
         tcyl = np.full(dx1.shape, np.inf)
         for cxs in (-3.5, 3.5):
@@ -88,8 +97,7 @@ def corridor(width: int, height: int, *, frame: int = 0, seed: int = 0xA0, noise
                 tc = np.where(disc > 0, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), np.inf)
                 tcyl = np.minimum(tcyl, np.where(tc > 0, tc, np.inf))
         t = np.minimum(t, tcyl[None, :])
-    ys, xs = np.meshgrid(np.arange(row0, row1, dtype=np.uint64), np.arange(width, dtype=np.uint64), indexing="ij")
-    h = _pcg_hash(xs + np.uint64(width) * ys, seed + frame * 7919)
+    h = _pcg_hash(idx, seed + frame * 7919)
     z = t * (1.0 + noise * (h.astype(np.float64) / 4294967296.0 - 0.5))
     return (z / far).astype(np.float32)
 
