@@ -180,6 +180,104 @@ __device__ __forceinline__ float2 bilateral2(float2 hd, float2 ha,
     return div2_fast_neg(num, __fmul2_rn(total, m1));
 }
 
+// ---- phase-4 restructure (MEAO_UPS_V2, default on) ------------------------------------------------------------------
+// The kernel is issue-bound and the bilateral upsample is 62 % of its issue slots, so phase 4 was rebuilt around the slot count:
+//   * a real 2-iteration loop over the thread's two 4-pixel halves (pairs (0,2) (1,3) | (4,6) (5,7)): half the live low-res
+//     operands, no register spills under the 48-register cap, half the code;
+//   * the range test of the final division is proven on the host from the two tolerances (what MEAO_UPS_STATIC_GUARD did) and
+//     the one remaining run-time test -- every b_i finite and below 2^60 -- is accumulated as ONE integer max over the sign-
+//     ordered bit patterns of the four pair sums (a NaN, -inf or too large a sum has a larger signed pattern than -2^60);
+//   * w2 = 1 / b2 is the packed reciprocal (two roundings fewer instructions than the division; both are the correctly
+//     rounded 1 / b2, so the bits are the same);
+//   * the last step of the final division is issued as two FFMA.SAT (the saturate of the UNORM8 store rides on it) and the
+//     + 0.5 of the store conversion runs packed.
+// Threads that fail the test (sky: inf / NaN / zero / denormal operands), partial row ends and parameter sets outside the
+// proven range take upsample8_slow(): the plain IEEE operators, out of line.
+#ifndef MEAO_UPS_V2
+#define MEAO_UPS_V2 1
+#endif
+
+// sign-ordered pattern of a NEGATIVE float: more negative (or NaN = 0x7fffffff) => larger signed integer
+__device__ __forceinline__ int neg_order(float x) { return (int)__float_as_uint(x); }
+
+template <bool BLEND>
+__device__ __forceinline__ uint32_t bilateral2_v2(float2 hd, float2 ha,
+                                                  float2 ld0, float2 ld1, float2 ld2, float2 ld3,
+                                                  float2 la0, float2 la1, float2 la2, float2 la3,
+                                                  float tol, float nfs, int &worst)
+{
+    const float2 m1 = make_float2(-1.0f, -1.0f);
+    const float2 t0 = __ffma2_rn(ld0, m1, hd), t1 = __ffma2_rn(ld1, m1, hd);          // hd - ld_i (one rounding, == FADD)
+    const float2 t2 = __ffma2_rn(ld2, m1, hd), t3 = __ffma2_rn(ld3, m1, hd);
+    const float2 nb0 = make_float2(__fadd_rn(-fabsf(t0.x), -tol), __fadd_rn(-fabsf(t0.y), -tol));
+    const float2 nb1 = make_float2(__fadd_rn(-fabsf(t1.x), -tol), __fadd_rn(-fabsf(t1.y), -tol));
+    const float2 nb2 = make_float2(__fadd_rn(-fabsf(t2.x), -tol), __fadd_rn(-fabsf(t2.y), -tol));
+    const float2 nb3 = make_float2(__fadd_rn(-fabsf(t3.x), -tol), __fadd_rn(-fabsf(t3.y), -tol));
+    const float2 s = __fadd2_rn(__fadd2_rn(nb0, nb1), __fadd2_rn(nb2, nb3));
+    worst = max(max(worst, neg_order(s.x)), neg_order(s.y));                          // guard of bilateral<true>: s > -2^60, finite
+    const float2 w0 = div2_fast_neg(make_float2(9.0f, 9.0f), nb0);
+    const float2 w1 = div2_fast_neg(make_float2(3.0f, 3.0f), nb1);
+    const float2 w2 = rcp2_fast_neg(nb2);                                             // RN(1 / b2) == div_fast(1, b2)
+    const float2 w3 = div2_fast_neg(make_float2(3.0f, 3.0f), nb3);
+    const float2 nfs2 = make_float2(nfs, nfs);
+    const float2 total = __fadd2_rn(__fadd2_rn(__fadd2_rn(__fadd2_rn(w0, w1), w2), w3), nfs2);
+    const float2 wsum = __fadd2_rn(__ffma2_rn(la3, w3, __ffma2_rn(la2, w2, __ffma2_rn(la1, w1, __fmul2_rn(la0, w0)))), nfs2);
+    const float2 num = BLEND ? __fmul2_rn(ha, wsum) : wsum;
+    // num / total, lane-wise div_fast; the host has proven total and num inside the fast-division range (UpsampleArgs.fast_div_ok,
+    // see the MEAO_UPS_STATIC_GUARD note in bilateral2), the saturate of the store conversion is fused into the last FMA
+    const float2 nden = __fmul2_rn(total, m1);
+    float2 y = make_float2(rcp_approx(total.x), rcp_approx(total.y));
+    const float2 e = __ffma2_rn(nden, y, make_float2(1.0f, 1.0f));
+    y = __ffma2_rn(y, e, y);
+    const float2 q = __fmul2_rn(num, y);
+    const float2 r = __ffma2_rn(nden, q, num);
+    const float2 c = make_float2(__saturatef(fmaf(y.x, r.x, q.x)), __saturatef(fmaf(y.y, r.y, q.y)));
+    // unorm8_code: c * 255 and + 0.5 are TWO roundings.  ptxas contracts a packed mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2
+    // (seen in the SASS; the explicit .rn does not protect the packed forms), so the product stays scalar -- mul.rn.f32 is never fused
+    const float2 k = __fadd2_rn(make_float2(__fmul_rn(c.x, 255.0f), __fmul_rn(c.y, 255.0f)), make_float2(0.5f, 0.5f));
+    return (uint32_t)k.x | ((uint32_t)k.y << 16);                                     // codes of pixels E (bits 0..7) and E + 2 (bits 16..23)
+}
+
+// The rare path: all eight pixels of a thread with the plain IEEE operators (UPS:177-183, 229-232), partial rows included.
+// (scalar arguments, not the argument block by reference: taking its address would force a local-memory copy of the kernel parameters)
+template <bool BLEND, bool HI_HALF>
+__device__ __noinline__ void upsample8_slow(const void *hi_depth, int hi_dpitch, const uint8_t *hi_ao, int hi_apitch, uint8_t *out, int out_pitch,
+                                            int out_row_origin, int hiw, float tol, float nfs,
+                                            const float *vblur, const float *lo_depth, int rY, int j, int py, int px0)
+{
+    float bl_ao[2][6], lo_d[2][6];
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            bl_ao[rr][i] = vblur[(rY - 1 + rr) * kBlurP + 4 * j + i];
+            lo_d[rr][i] = lo_depth[(rY - 1 + rr + 2) * kLoDP + 4 * j + 2 + i];
+        }
+    const bool y_odd = (py & 1) != 0;
+    uint8_t *dst = out + (size_t)(py - out_row_origin) * out_pitch + px0;
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) {
+        if (px0 + e >= hiw) break;
+        float hd, ha = 1.0f;                                                                                     // UPS:223
+        if (HI_HALF) hd = __half2float(reinterpret_cast<const __half *>(hi_depth)[(size_t)py * hi_dpitch + px0 + e]);
+        else hd = __ldg(reinterpret_cast<const float *>(hi_depth) + (size_t)py * hi_dpitch + px0 + e);
+        if (BLEND) ha = unorm8_load(__ldg(hi_ao + (size_t)py * hi_apitch + px0 + e));
+        const int m = (e + 1) >> 1;
+        const float tl_d = lo_d[0][m], tr_d = lo_d[0][m + 1], bl_d = lo_d[1][m], br_d = lo_d[1][m + 1];
+        const float tl_a = bl_ao[0][m], tr_a = bl_ao[0][m + 1], bl_a = bl_ao[1][m], br_a = bl_ao[1][m + 1];
+        bool unused = true;
+        float r;
+        if ((e & 1) != 0) {
+            if (!y_odd) r = bilateral<false, BLEND>(hd, ha, bl_d, br_d, tr_d, tl_d, bl_a, br_a, tr_a, tl_a, tol, nfs, unused);   // UPS:229
+            else        r = bilateral<false, BLEND>(hd, ha, tl_d, bl_d, br_d, tr_d, tl_a, bl_a, br_a, tr_a, tol, nfs, unused);   // UPS:232
+        } else {
+            if (!y_odd) r = bilateral<false, BLEND>(hd, ha, br_d, tr_d, tl_d, bl_d, br_a, tr_a, tl_a, bl_a, tol, nfs, unused);   // UPS:230
+            else        r = bilateral<false, BLEND>(hd, ha, tr_d, tl_d, bl_d, br_d, tr_a, tl_a, bl_a, br_a, tol, nfs, unused);   // UPS:231
+        }
+        dst[e] = (uint8_t)unorm8_code(r);
+    }
+}
+
 #ifndef MEAO_UPS_MINB
 #define MEAO_UPS_MINB 5
 #endif

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) halo_copy_kernel(const HaloArgs a)
 #ifdef MEAO_DEVICE_OK
     const HaloSeg s = a.seg[blockIdx.y];
     const int n = s.rows * s.width;
+    pdl_wait();                     // the pack reads rows prepare_depth (the preceding grid) has just written
+    pdl_launch_dependents();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int r = i / s.width, c = i - r * s.width;
         s.dst[(size_t)r * s.dst_pitch + c] = s.src[(size_t)r * s.src_pitch + c];

@@ -14,6 +14,11 @@
 #ifndef MEAO_UPS_STATIC_GUARD
 #define MEAO_UPS_STATIC_GUARD 0
 #endif
+// Build switch: the restructured bilateral-upsample phase (blur_upsample.cu, "phase-4 restructure"); it relies on the same
+// host-side proof as MEAO_UPS_STATIC_GUARD, so the planner applies the tighter tolerance bounds whenever either is on.
+#ifndef MEAO_UPS_V2
+#define MEAO_UPS_V2 1
+#endif
 
 #ifdef MEAO_EMULATE              // tests/emu only (see common.cuh)
 #include "cuda_emu.h"

@@ -515,10 +515,10 @@ int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
     {
         auto safe = [](float x) { return x >= 8.673617379884035e-19f && x < 1152921504606846976.0f; };
         a.fast_div_ok = safe(a.upsample_tolerance) && safe(a.noise_filter_strength);
-#if MEAO_UPS_STATIC_GUARD
+#if MEAO_UPS_STATIC_GUARD || MEAO_UPS_V2
         // 2^-55, 2^-52, 2^59: with these bounds total / num of the final division are provably inside the fast-division range
         a.fast_div_ok = a.fast_div_ok && a.upsample_tolerance >= 2.7755575615628914e-17f &&
-                        a.noise_filter_strength >= 2.220446049250313e-16f && a.noise_filter_strength < 576460752303423488.0f;
+                        a.noise_filter_strength >= 2.220446049250313e-16f && a.noise_filter_strength < 288230376151711744.0f;
 #endif
     }
     a.row0 = c->need_c[hi].lo; a.row1 = c->need_c[hi].hi;

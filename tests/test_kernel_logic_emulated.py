@@ -174,7 +174,7 @@ def test_debug_composite_pass3():
 
 
 @pytest.mark.parametrize("defs", [
-    ("-DMEAO_PACKED_RCP=0",), ("-DMEAO_UPS_STATIC_GUARD=1",), ("-DMEAO_REN_CLAMP_MODE=0",), ("-DMEAO_REN_CLAMP_MODE=2",),
+    ("-DMEAO_PACKED_RCP=0",), ("-DMEAO_UPS_V2=0", "-DMEAO_UPS_STATIC_GUARD=1"), ("-DMEAO_UPS_V2=0",), ("-DMEAO_REN_CLAMP_MODE=0",), ("-DMEAO_REN_CLAMP_MODE=2",),
 ])
 def test_build_switches_keep_the_arithmetic(defs):
     """Every tuning switch of the kernels (csrc/common.cuh, kernels.h, render_ao.cu) must leave all results unchanged."""
@@ -284,3 +284,8 @@ def test_native_exchange_times_out_instead_of_hanging():
     b.flags(set_ready_ack=(0, 0, 1, 0))                          # ack from a, but a's rows "never arrive"
     assert b.exchange(a, None, timeout_polls=50) == 2
     assert b.flags()["host_error"] == 2
+
+
+def test_tolerances_outside_the_proven_range_take_the_ieee_path():
+    """fast_div_ok = 0 (upsample tolerance 10^-17 < 2^-55): the whole upsample runs upsample8_slow."""
+    _run(161, 93, seed=21, upsample_tolerance=-17.0, noise_filter_tolerance=-8.0, intensity=1.2)
