@@ -198,6 +198,7 @@ def run_ours(args) -> None:
     K, Wm = max(1, args.steps), max(args.warmup, 3)
     NBUF = 8
     S = max(1, args.streams)
+    BAND_ONLY = args.only_8k
 
     def barrier():
         if world > 1:
@@ -257,6 +258,15 @@ def run_ours(args) -> None:
             submit(i)
         ms = timed_batches(submit, sts, k)
         return statistics.median(ms), ms, ctxs, sts, submit
+
+    if BAND_ONLY:       # development aid: just the row-banded 8K measurement (not a bench line the driver uses)
+        peak, _ = load_peaks()
+        r = bench_8k(args, torch, dist if world > 1 else None, dev, rank, world, local, barrier, allmax, timed_batches, mk_contexts, peak)
+        if rank == 0:
+            print(json.dumps(r), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ================= headline: 4K (or --workload) frames, device resident =================================================
     frames_host = [make_depth(W, H, f + 64 * rank) for f in range(2)]
@@ -657,6 +667,7 @@ def main() -> None:
     ap.add_argument("--quick", action="store_true", help="headline + e2e + roofline only (skip the other configs and the composite)")
     ap.add_argument("--streams", type=int, default=5, help="contexts/streams that frames alternate over in throughput mode")
     ap.add_argument("--band-streams", type=int, default=3, help="band contexts per rank in the row-tiled 8K measurement")
+    ap.add_argument("--only-8k", action="store_true", help="development aid: only the 8K single-frame / row-band measurement")
     ap.add_argument("--band-mode", default="native", choices=["native", "p2p"], help="halo exchange: peer stores inside the graph / NCCL send-recv between two graphs")
     args = ap.parse_args()
     if args.impl == "reference":
