@@ -262,6 +262,12 @@ int meao_band_export(MeaoCtx *ctx, MeaoPeerHandle *out);
  * another process: cudaIpcOpenMemHandle.  Fails with MEAO_ERR_INVALID if the neighbour's frame size differs. */
 int meao_band_connect(MeaoCtx *ctx, int32_t side, const MeaoPeerHandle *peer);
 int meao_band_step(MeaoCtx *ctx, const void *depth_band_dev, int32_t depth_kind, void *ao_band_out_dev, void *stream);
+/* The same with HOST buffers (the band's rows only): H2D copy, the step, D2H copy, all enqueued on the context's staging slot 0 --
+ * asynchronous, because the neighbours' steps must be enqueued too before anyone waits; then meao_host_wait(ctx, 0) on every band.
+ * The host buffers MUST be pinned (meao_host_alloc): a pageable copy blocks the calling thread until it has completed, which it
+ * cannot before the neighbour -- not yet enqueued by that same thread -- has taken part in the exchange.
+ * This is what lets a single-threaded C / C# host drive all GPUs of a box (tests/c_abi/smoke.c "bands"). */
+int meao_band_step_host(MeaoCtx *ctx, const void *depth_band_host, int32_t depth_kind, uint8_t *ao_band_out_host);
 /* out4 = { epoch of the next exchange (1 + completed exchanges), sticky error (0 ok, 1 = time-out waiting for a neighbour's
  * ack, 2 = time-out waiting for a neighbour's rows), connected-up, connected-down }.  Synchronises nothing: reads the
  * flags with a stream-less copy, so call it after the stream has drained for a definitive answer. */

@@ -95,6 +95,7 @@ SIGNATURES = {
     "meao_band_export": (C.c_int, [C.c_void_p, C.POINTER(MeaoPeerHandle)]),
     "meao_band_connect": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(MeaoPeerHandle)]),
     "meao_band_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "meao_band_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "meao_band_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "meao_bind_event": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "meao_render_event": (None, [C.c_int]),

@@ -278,6 +278,14 @@ __device__ __noinline__ void upsample8_slow(const void *hi_depth, int hi_dpitch,
     }
 }
 
+// Run lengths of the two blur passes (outputs per thread and lane).  Longer runs share more depth deltas between neighbouring
+// outputs (fewer instructions in total), shorter runs put more of the CTA's eight warps to work and shorten the phase.
+#ifndef MEAO_UPS_HRUN
+#define MEAO_UPS_HRUN 4         // 4: 99 threads; 2: 187 threads
+#endif
+#ifndef MEAO_UPS_VRUN
+#define MEAO_UPS_VRUN 6         // 6: 51 threads; 3: 102 threads; 2: 153 threads
+#endif
 #ifndef MEAO_UPS_MINB
 #define MEAO_UPS_MINB 5
 #endif

@@ -418,15 +418,16 @@ int ensure_ready(MeaoCtx *c)
 struct NvtxRange { explicit NvtxRange(const char *n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } };
 
 // Tile-height variant (index into kRenderTileHs = {32, 16, 8}) of a render launch.  The big levels keep the 64 x 32 tile
-// (least apron overhead: throughput); a level whose grid would not put two CTAs on every SM is latency-bound -- one
-// CTA's serial time IS the kernel time -- so it takes the tallest tile that still gives >= 2 x 148 CTAs, else 64 x 8.
+// (least apron overhead: throughput); a level whose grid would not even put one CTA on every SM is latency-bound -- one
+// CTA's serial time IS the kernel time -- so it takes the tallest tile that still gives >= 148 CTAs, else 64 x 8.
+// (Measured at 4K: level 2, 255 CTAs of 64 x 32, is FASTER with the big tile -- 14.0 vs 15.7 us -- levels 3 / 4 gain ~0.5 us.)
 int render_tile_variant(const MeaoCtx *c, int k, int rows)
 {
     const char *force = getenv("MEAO_REN_TILE");               // tuning aid: 0 / 1 / 2 forces a variant for every level
     if (force && force[0] >= '0' && force[0] < '0' + kRenderTileVariants) return force[0] - '0';
     for (int t = 0; t < kRenderTileVariants; t++) {
         const int ctas = ((c->lw[k] + 63) / 64) * ((rows + kRenderTileHs[t] - 1) / kRenderTileHs[t]);
-        if (ctas >= 2 * 148) return t;
+        if (ctas >= 148) return t;
     }
     return kRenderTileVariants - 1;
 }
@@ -1148,6 +1149,20 @@ int meao_band_step(MeaoCtx *c, const void *depth, int32_t kind, void *ao_out, vo
         { PdlScope p(pdl >= 1); if ((r = record_exchange(c, s))) return r; }
         return record_frame_dag(c, nullptr, kind, ao_out, s, false, pdl, has_peer);
     });
+}
+
+int meao_band_step_host(MeaoCtx *c, const void *depth_host, int32_t kind, uint8_t *ao_host)
+{
+    int rc = ensure_ready(c); if (rc) return rc;
+    if (!depth_host || !ao_host) return fail(c, MEAO_ERR_INVALID, "depth / ao_out is NULL");
+    if (kind < MEAO_DEPTH_RAW_F32 || kind > MEAO_DEPTH_RAW_D24S8) return fail(c, MEAO_ERR_INVALID, "bad depth kind %d", kind);
+    const size_t rows = (size_t)(c->band1 - c->band0);
+    cudaStream_t s = c->slot_stream[0];
+    const size_t esz = (kind == MEAO_DEPTH_RAW_D16_UNORM) ? 2 : 4;
+    CUDA_TRY(c, cudaMemcpyAsync(c->depth_stage[0], depth_host, rows * c->W * esz, cudaMemcpyHostToDevice, s));
+    if ((rc = meao_band_step(c, c->depth_stage[0], kind, c->ao_stage[0], s))) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(ao_host, c->ao_stage[0], rows * c->W, cudaMemcpyDeviceToHost, s));
+    return MEAO_OK;
 }
 
 int meao_band_status(MeaoCtx *c, int32_t out4[4])

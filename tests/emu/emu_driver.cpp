@@ -122,7 +122,7 @@ static void run_render(Emu *e, int k, bool wide)
     if (tv < 0) {           // meao_api.cu render_tile_variant
         const int rows = a.row1 - (a.row0 & ~3);
         for (tv = 0; tv < kRenderTileVariants - 1; tv++)
-            if (((e->lw[k] + 63) / 64) * ((rows + kRenderTileHs[tv] - 1) / kRenderTileHs[tv]) >= 2 * 148) break;
+            if (((e->lw[k] + 63) / 64) * ((rows + kRenderTileHs[tv] - 1) / kRenderTileHs[tv]) >= 148) break;
     }
     a.tile_h = kRenderTileHs[tv];
     const CUtensorMap map = make_map(e->low[k], 4, e->lw[k], e->lh[k], e->low_pitch[k], wide ? kRenderWideBoxW : kRenderBoxW, render_box_h(a.tile_h, wide));

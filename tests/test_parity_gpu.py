@@ -992,3 +992,26 @@ def test_tolerances_outside_the_proven_range_take_the_ieee_path(torch_cuda):
     ref = orc.run(depth)
     assert np.array_equal(ao.render(torch.from_numpy(depth).cuda()).cpu().numpy(), ref)
     _compare_all(ao, orc, "slow path")
+
+
+def test_pure_c_client_drives_row_bands(torch_cuda, tmp_path):
+    """Multi-GPU from plain C ("a C#/C caller of include/meao.h cannot do multi-GPU at all"): tests/c_abi/smoke.c splits
+    a 1280 x 720 frame into 2 / 3 row bands, connects them with meao_band_export / meao_band_connect and steps them with
+    meao_band_step_host -- one single-threaded process, no NCCL, no Python.  All bands share device 0 here; with more devices the
+    same binary spreads them (last argument)."""
+    import os, subprocess
+    from test_abi import _build_c_client
+    from miniengineao_b200 import synth
+    from oracle.oracle import Oracle
+    torch = torch_cuda
+    W, H = 1280, 720
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    ref = Oracle(W, H, threads=8, intensity=1.1).run(depth)
+    dpath, apath = os.path.join(str(tmp_path), "depth.f32"), os.path.join(str(tmp_path), "ao.u8")
+    depth.tofile(dpath); ref.tofile(apath)
+    exe = _build_c_client(tmp_path)
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    ndev = min(torch.cuda.device_count(), 2)
+    for nb, nd in ((2, 1), (3, 1), (2, ndev)):
+        r = subprocess.run([exe, "bands", str(W), str(H), dpath, apath, "1.1", str(nb), str(nd)], capture_output=True, text=True, env=env, timeout=120)
+        assert r.returncode == 0 and " 0 mismatching pixels" in r.stdout, r.stdout + r.stderr
