@@ -7,10 +7,16 @@
  * Each function cites the reference lines it follows; paths are relative to
  * /root/reference/Assets/MiniEngineAO/.
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE          /* syscall(), for the worker pool's futex waits */
+#endif
 #include "meao_oracle.h"
 
+#include <linux/futex.h>
 #include <math.h>
 #include <pthread.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -305,47 +311,62 @@ void meao_oracle_upsample_constants(const MeaoOracle *o, int lo_level,
  * ---------------------------------------------------------------------------------------- */
 typedef void (*stripe_fn)(void *ctx, int gy0, int gy1);
 
-/* A persistent worker pool (the first version created and joined `threads` pthreads for every one of the ten stages of a frame,
- * which at 128 threads cost about as much as the arithmetic).  Work is handed out in chunks of thread-group rows through an
- * atomic cursor; rows are independent, so the result does not depend on the thread count or on who runs which chunk. */
+/* A persistent worker pool (the first version created and joined `threads` pthreads for every one of the ten stages of a frame).
+ * Workers sleep on a futex word (no mutex to re-acquire: all of them wake in parallel), take chunks of thread-group rows through an
+ * atomic cursor, and the last one to finish wakes the caller.  Rows are independent, so the result does not depend on the thread
+ * count or on who runs which chunk. */
 #define POOL_MAX 512
 static struct {
-    pthread_mutex_t region;             /* one parallel region at a time */
-    pthread_mutex_t mu;
-    pthread_cond_t go, done;
+    pthread_mutex_t region;                     /* one parallel region at a time */
     pthread_t tid[POOL_MAX];
-    int nworkers;                       /* threads created so far */
-    unsigned long generation;
-    int active;                         /* workers taking part in the current region */
-    int running;                        /* workers that have not finished the current region yet */
-    stripe_fn fn; void *ctx; int ny, chunk;
+    int nworkers;                               /* threads created so far */
+    stripe_fn fn; void *ctx; int ny, chunk, active, xparts;
+    char pad0[64];
+    volatile int generation;                    /* futex word: bumped once per region */
+    char pad1[60];
+    volatile int running;                       /* futex word: workers that have not finished the current region */
+    char pad2[60];
     volatile int cursor;
-} g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER,
-             {0}, 0, 0, 0, 0, NULL, NULL, 0, 1, 0 };
+    char pad3[60];
+} g_pool = { .region = PTHREAD_MUTEX_INITIALIZER };
+
+static long pool_futex(volatile int *addr, int op, int val) { return syscall(SYS_futex, addr, op, val, NULL, NULL, 0); }
+
+/* When a stage has fewer thread-group rows than ~4 per thread (the two big stages of a 4K frame have 135 rows: on 128 threads a
+ * pure row split leaves half the cores idle), every row is additionally cut into `xparts` column ranges; the stripe functions read
+ * their range through XLO / XHI. */
+static __thread int t_xpart = 0, t_xparts = 1;
+#define XLO(n) ((int)((long long)(n) * t_xpart / t_xparts))
+#define XHI(n) ((int)((long long)(n) * (t_xpart + 1) / t_xparts))
 
 static void pool_drain(void)
 {
+    const int xparts = g_pool.xparts, units = g_pool.ny * xparts;
     for (;;) {
-        int g0 = __atomic_fetch_add(&g_pool.cursor, g_pool.chunk, __ATOMIC_RELAXED);
-        if (g0 >= g_pool.ny) return;
-        int g1 = g0 + g_pool.chunk; if (g1 > g_pool.ny) g1 = g_pool.ny;
-        g_pool.fn(g_pool.ctx, g0, g1);
+        int u0 = __atomic_fetch_add(&g_pool.cursor, g_pool.chunk, __ATOMIC_RELAXED);
+        if (u0 >= units) break;
+        if (xparts == 1) {
+            int u1 = u0 + g_pool.chunk; if (u1 > units) u1 = units;
+            g_pool.fn(g_pool.ctx, u0, u1);
+        } else {                                    /* chunk == 1: one (row, column range) unit at a time */
+            t_xpart = u0 % xparts; t_xparts = xparts;
+            g_pool.fn(g_pool.ctx, u0 / xparts, u0 / xparts + 1);
+        }
     }
+    t_xpart = 0; t_xparts = 1;
 }
 
 static void *pool_worker(void *arg)
 {
     const int index = (int)(intptr_t)arg;
-    unsigned long seen = 0;
-    pthread_mutex_lock(&g_pool.mu);
+    int seen = 0;
     for (;;) {
-        while (g_pool.generation == seen) pthread_cond_wait(&g_pool.go, &g_pool.mu);
-        seen = g_pool.generation;
+        int g;
+        while ((g = __atomic_load_n(&g_pool.generation, __ATOMIC_ACQUIRE)) == seen) pool_futex(&g_pool.generation, FUTEX_WAIT_PRIVATE, seen);
+        seen = g;
         if (index >= g_pool.active) continue;
-        pthread_mutex_unlock(&g_pool.mu);
         pool_drain();
-        pthread_mutex_lock(&g_pool.mu);
-        if (--g_pool.running == 0) pthread_cond_signal(&g_pool.done);
+        if (__atomic_sub_fetch(&g_pool.running, 1, __ATOMIC_ACQ_REL) == 0) pool_futex(&g_pool.running, FUTEX_WAKE_PRIVATE, 1);
     }
     return NULL;
 }
@@ -353,11 +374,10 @@ static void *pool_worker(void *arg)
 static void run_striped(stripe_fn fn, void *ctx, int ny, int threads)
 {
     if (threads < 1) threads = 1;
-    if (threads > ny) threads = ny > 0 ? ny : 1;
+    if (threads > ny * 16) threads = ny > 0 ? ny * 16 : 1;
     if (threads > POOL_MAX) threads = POOL_MAX;
-    if (threads == 1) { fn(ctx, 0, ny); return; }
+    if (threads == 1 || ny <= 0) { if (ny > 0) fn(ctx, 0, ny); return; }
     pthread_mutex_lock(&g_pool.region);
-    pthread_mutex_lock(&g_pool.mu);
     while (g_pool.nworkers < threads - 1) {                 /* the calling thread is worker number `threads` */
         pthread_attr_t at; pthread_attr_init(&at); pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
         if (pthread_create(&g_pool.tid[g_pool.nworkers], &at, pool_worker, (void *)(intptr_t)g_pool.nworkers) != 0) { pthread_attr_destroy(&at); break; }
@@ -365,17 +385,21 @@ static void run_striped(stripe_fn fn, void *ctx, int ny, int threads)
         g_pool.nworkers++;
     }
     g_pool.fn = fn; g_pool.ctx = ctx; g_pool.ny = ny;
-    g_pool.chunk = (ny + threads * 4 - 1) / (threads * 4); if (g_pool.chunk < 1) g_pool.chunk = 1;
+    g_pool.chunk = ny / (threads * 4); if (g_pool.chunk < 1) g_pool.chunk = 1;
+    g_pool.xparts = (ny >= threads * 4) ? 1 : (threads * 4 + ny - 1) / ny;
+    if (g_pool.xparts > 16) g_pool.xparts = 16;
+    if (g_pool.xparts > 1) g_pool.chunk = 1;
     g_pool.cursor = 0;
     g_pool.active = g_pool.nworkers < threads - 1 ? g_pool.nworkers : threads - 1;
-    g_pool.running = g_pool.active;
-    g_pool.generation++;
-    pthread_cond_broadcast(&g_pool.go);
-    pthread_mutex_unlock(&g_pool.mu);
+    __atomic_store_n(&g_pool.running, g_pool.active, __ATOMIC_RELEASE);
+    __atomic_add_fetch(&g_pool.generation, 1, __ATOMIC_ACQ_REL);
+    pool_futex(&g_pool.generation, FUTEX_WAKE_PRIVATE, POOL_MAX);
     pool_drain();
-    pthread_mutex_lock(&g_pool.mu);
-    while (g_pool.running > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
-    pthread_mutex_unlock(&g_pool.mu);
+    for (;;) {
+        int r = __atomic_load_n(&g_pool.running, __ATOMIC_ACQUIRE);
+        if (r == 0) break;
+        pool_futex(&g_pool.running, FUTEX_WAIT_PRIVATE, r);
+    }
     pthread_mutex_unlock(&g_pool.region);
 }
 
@@ -412,7 +436,7 @@ static void ds1_stripe(void *vc, int gy0, int gy1)
     const int A1w = o->lw[3], A1h = o->lh[3], A2w = o->lw[4], A2h = o->lh[4];
     float cache[256];                                                    /* DS1:50 g_CacheW */
     for (int gy = gy0; gy < gy1; gy++)
-    for (int gx = 0; gx < o->lw[4]; gx++) {
+    for (int gx = XLO(o->lw[4]); gx < XHI(o->lw[4]); gx++) {
         for (int ty = 0; ty < 8; ty++) for (int tx = 0; tx < 8; tx++) {
             int sx = (gx << 4) | tx, sy = (gy << 4) | ty;                /* DS1:55 */
             int dest = (ty << 4) | tx;                                   /* DS1:56 */
@@ -449,7 +473,7 @@ static void ds2_stripe(void *vc, int gy0, int gy1)
     const int L2w = o->lw[2], L2h = o->lh[2], L3w = o->lw[3], L3h = o->lh[3], L4w = o->lw[4], L4h = o->lh[4];
     const int A3w = o->lw[5], A3h = o->lh[5], A4w = o->lw[6], A4h = o->lh[6];
     for (int gy = gy0; gy < gy1; gy++)
-    for (int gx = 0; gx < o->lw[6]; gx++)
+    for (int gx = XLO(o->lw[6]); gx < XHI(o->lw[6]); gx++)
     for (int ty = 0; ty < 8; ty++) for (int tx = 0; tx < 8; tx++) {
         int GI = ty * 8 + tx;
         int stx = gx * 8 + tx, sty = gy * 8 + ty;
@@ -572,7 +596,7 @@ static void ren_stripe(void *vc, int r0, int r1)
     for (int r = r0; r < r1; r++) {
         int z = r / ngy, gy = r % ngy;
         const float *slice = o->tiled_depth[k] + (size_t)z * sw * sh;
-        for (int gx = 0; gx < ngx; gx++) {
+        for (int gx = XLO(ngx); gx < XHI(ngx); gx++) {
             for (int ty = 0; ty < 8; ty++) for (int tx = 0; tx < 8; tx++) {
                 int cx = gx * 8 + tx + tx - 3, cy = gy * 8 + ty + ty - 3;            /* REN:118 (DTid + GTid - 3) * invDim */
                 float4_t d = gather4(slice, sw, sh, cx, cy);                         /* REN:123 */
@@ -614,7 +638,7 @@ static void ren_wide_stripe(void *vc, int gy0, int gy1)
     const float *src = o->low_depth[k];
     float DS[REN_TILE_DIM_WIDE * REN_TILE_DIM_WIDE];                                 /* REN:58 */
     for (int gy = gy0; gy < gy1; gy++)
-    for (int gx = 0; gx < ngx; gx++) {
+    for (int gx = XLO(ngx); gx < XHI(ngx); gx++) {
         for (int ty = 0; ty < 16; ty++) for (int tx = 0; tx < 16; tx++) {
             int cx = gx * 16 + tx + tx - 7, cy = gy * 16 + ty + ty - 7;              /* REN:116 (DTid + GTid - 7) * invDim */
             float4_t d = gather4(src, sw, sh, cx, cy);                               /* REN:125 */
@@ -734,7 +758,7 @@ static void ups_stripe(void *vc, int gy0, int gy1)
     const int ngx = (c->hiw + 17) / 16;
     float DC[256], AO1[256], AO2[256];                                   /* UPS:50-52 */
     for (int gy = gy0; gy < gy1; gy++)
-    for (int gx = 0; gx < ngx; gx++) {
+    for (int gx = XLO(ngx); gx < XHI(ngx); gx++) {
         memset(AO2, 0, sizeof(AO2));   /* row 13 is read (UPS:139) but never written; feeds only an unconsumed output */
         for (int ty = 0; ty < 8; ty++) for (int tx = 0; tx < 8; tx++) {
             unsigned index = (unsigned)((tx << 1) | (ty << 5));          /* UPS:191 */
