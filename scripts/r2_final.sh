@@ -58,6 +58,5 @@ for tool in memcheck racecheck; do
   echo "== compute-sanitizer --tool $tool (330x170 frame + single-scale)" >> ${T}_compute_sanitizer.txt
   timeout 600 compute-sanitizer --tool $tool python /tmp/san.py 2>&1 | grep -E "matches|ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" | head -12 >> ${T}_compute_sanitizer.txt
 done
-echo "== compute-sanitizer --tool memcheck (two connected bands, native exchange, MEAO_BAND_TIMEOUT_MS=60000)" >> ${T}_compute_sanitizer.txt
-MEAO_BAND_TIMEOUT_MS=60000 CUDA_DEVICE_MAX_CONNECTIONS=32 timeout 900 compute-sanitizer --tool memcheck python /tmp/san.py bands 2>&1 | grep -E "match|ERROR SUMMARY|Error" | head -12 >> ${T}_compute_sanitizer.txt
+echo "(the native exchange is not run under the sanitizer: it serialises kernels, and two neighbouring bands on ONE GPU need their exchange kernels resident together -- the run ends in the kernel's own time-out, error 1, as designed)" >> ${T}_compute_sanitizer.txt
 cat ${T}_compute_sanitizer.txt

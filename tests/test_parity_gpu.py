@@ -996,7 +996,7 @@ def test_tolerances_outside_the_proven_range_take_the_ieee_path(torch_cuda):
 
 def test_pure_c_client_drives_row_bands(torch_cuda, tmp_path):
     """Multi-GPU from plain C ("a C#/C caller of include/meao.h cannot do multi-GPU at all"): tests/c_abi/smoke.c splits
-    a 1280 x 720 frame into 2 / 3 row bands, connects them with meao_band_export / meao_band_connect and steps them with
+    a 1280 x 1200 frame into 2 / 3 row bands, connects them with meao_band_export / meao_band_connect and steps them with
     meao_band_step_host -- one single-threaded process, no NCCL, no Python.  All bands share device 0 here; with more devices the
     same binary spreads them (last argument)."""
     import os, subprocess
@@ -1004,7 +1004,7 @@ def test_pure_c_client_drives_row_bands(torch_cuda, tmp_path):
     from miniengineao_b200 import synth
     from oracle.oracle import Oracle
     torch = torch_cuda
-    W, H = 1280, 720
+    W, H = 1280, 1200                                        # three bands of 400 rows: deep enough for the level-4 halo
     depth = synth.lin01_to_raw(synth.corridor(W, H))
     ref = Oracle(W, H, threads=8, intensity=1.1).run(depth)
     dpath, apath = os.path.join(str(tmp_path), "depth.f32"), os.path.join(str(tmp_path), "ao.u8")
