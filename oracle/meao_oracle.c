@@ -339,11 +339,12 @@ static __thread int t_xpart = 0, t_xparts = 1;
 #define XLO(n) ((int)((long long)(n) * t_xpart / t_xparts))
 #define XHI(n) ((int)((long long)(n) * (t_xpart + 1) / t_xparts))
 
-/* MEAO_ORACLE_POOL: 1 (default) = every worker owns a FIXED contiguous range of units, so a thread touches the same rows frame after
- * frame (first-touch NUMA locality, like the static row split of round 1, but balanced); 2 = units handed out through an atomic cursor
- * (best balance, no locality: measured 25 % slower than 0 on the two-socket 128-thread host); 0 = round 1: create + join per stage. */
+/* MEAO_ORACLE_POOL: 2 (default) = units handed out through an atomic cursor; 1 = every worker owns a FIXED contiguous range of units
+ * (a thread touches the same rows frame after frame); 0 = round 1: one pthread per row stripe, created and joined for every stage.
+ * On the two-socket 128-thread B200 host (shared with other tenants: medians are noisy), one 4K frame, best / median of 8 runs on 64
+ * threads: mode 0 166 / 126, mode 1 201 / 102, mode 2 245 / 102 Mpx/s (gpurun_out r2g, before the spin-then-sleep wait was added). */
 #ifndef MEAO_ORACLE_POOL
-#define MEAO_ORACLE_POOL 1
+#define MEAO_ORACLE_POOL 2
 #endif
 
 __attribute__((unused)) static void pool_run_unit_range(int u0, int u1)
@@ -386,7 +387,11 @@ __attribute__((unused)) static void *pool_worker(void *arg)
     int seen = 0;
     for (;;) {
         int g;
-        while ((g = __atomic_load_n(&g_pool.generation, __ATOMIC_ACQUIRE)) == seen) pool_futex(&g_pool.generation, FUTEX_WAIT_PRIVATE, seen);
+        /* the ten stages of a frame follow each other within microseconds: spin briefly before going to sleep */
+        for (int spin = 0; (g = __atomic_load_n(&g_pool.generation, __ATOMIC_ACQUIRE)) == seen; spin++) {
+            if (spin < 4000) __builtin_ia32_pause();
+            else pool_futex(&g_pool.generation, FUTEX_WAIT_PRIVATE, seen);
+        }
         seen = g;
         if (index >= g_pool.active) continue;
         pool_drain(index);
@@ -439,10 +444,11 @@ static void run_striped(stripe_fn fn, void *ctx, int ny, int threads)
     __atomic_add_fetch(&g_pool.generation, 1, __ATOMIC_ACQ_REL);
     pool_futex(&g_pool.generation, FUTEX_WAKE_PRIVATE, POOL_MAX);
     pool_drain(g_pool.active);
-    for (;;) {
+    for (int spin = 0;; spin++) {
         int r = __atomic_load_n(&g_pool.running, __ATOMIC_ACQUIRE);
         if (r == 0) break;
-        pool_futex(&g_pool.running, FUTEX_WAIT_PRIVATE, r);
+        if (spin < 4000) __builtin_ia32_pause();
+        else pool_futex(&g_pool.running, FUTEX_WAIT_PRIVATE, r);
     }
     pthread_mutex_unlock(&g_pool.region);
 }
