@@ -313,6 +313,10 @@ int64_t meao_algorithmic_bytes(const MeaoCtx *ctx, int32_t stage);
  * frame with a cudaEvent pair around every kernel.  names/ms arrays of length >= meao_kernels_per_frame(). */
 int meao_profile_frame(MeaoCtx *ctx, const void *depth_dev, int32_t depth_kind, void *ao_out_dev,
                        float *ms_out, const char **names_out, int32_t capacity);
+/* Launches per kernel inside meao_profile_frame's event pairs (default 1).  With n > 1 every kernel is launched n times back to back
+ * (all of them are idempotent: out of place, inputs untouched) and the reported time is the mean -- the event pair's own overhead and
+ * the launch gap are amortised, which is what a roofline figure of ONE kernel wants. */
+int meao_set_profile_repeats(MeaoCtx *ctx, int32_t n);
 
 /* Device self test: compares the guarded fast division / reciprocal the kernels use (MUFU.RCP + FMA
  * refinement, csrc/common.cuh) with the IEEE operators on n random operand pairs; *mismatches must be 0. */

@@ -105,6 +105,7 @@ SIGNATURES = {
     "meao_kernels_per_frame": (C.c_int, [C.c_void_p]),
     "meao_algorithmic_bytes": (C.c_int64, [C.c_void_p, C.c_int32]),
     "meao_selftest_div": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "meao_set_profile_repeats": (C.c_int, [C.c_void_p, C.c_int32]),
     "meao_profile_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float),
                                      C.POINTER(C.c_char_p), C.c_int32]),
 }

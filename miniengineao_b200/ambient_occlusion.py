@@ -483,8 +483,10 @@ class AmbientOcclusion:
         self._check(self._lib.meao_selftest_div(self._ctx, n, seed, C.byref(m)))
         return int(m.value)
 
-    def profile_frame(self, depth, out, *, linear: bool = False) -> list[tuple[str, float]]:
+    def profile_frame(self, depth, out, *, linear: bool = False, repeats: int = 1) -> list[tuple[str, float]]:
+        """(name, ms) per kernel of one serial frame; repeats > 1: every kernel launched that many times back to back, mean reported."""
         self._update(False)
+        self._check(self._lib.meao_set_profile_repeats(self._ctx, int(repeats)))
         n = self.kernels_per_frame
         ms = (C.c_float * n)()
         names = (C.c_char_p * n)()

@@ -49,17 +49,18 @@ constexpr int kThreads = 256;
 static_assert(kRawH == kUpsDepthBoxH && kRawH == kUpsAoBoxH, "TMA box mismatch");
 
 struct __align__(128) Smem {
-    alignas(128) float box_depth[kRawH * kBoxDP];   // TMA destination: low-res depth box (LoResDB)
-    alignas(128) uint8_t box_ao[kRawH * kBoxAP];    // TMA destination: low-res AO codes box (LoResAO1)
-    alignas(16) float lo_depth[kRawH * kLoDP];      // raw low-res depth, column 0 = virtual column lx0
+    alignas(128) float box_depth[2][kRawH * kBoxDP];    // TMA destination: low-res depth box (LoResDB); two copies: tile i+1 is prefetched while tile i is processed
+    alignas(128) uint8_t box_ao[2][kRawH * kBoxAP];     // TMA destination: low-res AO codes box (LoResAO1)
+    alignas(16) float lo_depth[2][kRawH * kLoDP];       // raw low-res depth, column 0 = virtual column lx0 (read until the end of phase 4: double-buffered)
     alignas(16) float inv_depth[kRawH * kRawP];     // DepthCache, UPS:67-71
     alignas(16) float ao[kRawH * kRawP];            // AOCache1 as loaded, UPS:62-65
     alignas(16) float hblur[kRawH * kBlurP];        // AOCache2, UPS:127-129
     alignas(16) float vblur[kBlurH * kBlurP];       // AOCache1 after the vertical pass, UPS:168-169
-    alignas(8) uint64_t bar;
+    alignas(8) uint64_t bar[2];
+    alignas(16) int4 tile[2];                       // this / the next iteration's tile, decoded by thread 0: hx0 (-1 = none), hy0, interior
 };
 struct SmemPremin : Smem {
-    alignas(128) uint8_t box_ao2[kRawH * kBoxAP];   // TMA destination: second low-res AO codes box (LoResAO2)
+    alignas(128) uint8_t box_ao2[2][kRawH * kBoxAP];    // TMA destination: second low-res AO codes box (LoResAO2)
 };
 
 // Upsample.compute:177-183 with the swizzled argument order of :229-232.
@@ -286,6 +287,13 @@ __device__ __noinline__ void upsample8_slow(const void *hi_depth, int hi_dpitch,
 #ifndef MEAO_UPS_VRUN
 #define MEAO_UPS_VRUN 6         // 6: 51 threads; 3: 102 threads; 2: 153 threads
 #endif
+#ifndef MEAO_UPS_V2_UNROLL
+#define MEAO_UPS_V2_UNROLL 0        // 1: both 4-pixel halves of phase 4 in flight (more ILP, more registers)
+#endif
+// Persistent tile loop with TMA prefetch of the next tile (see blur_upsample_kernel.inc); 0 = one CTA per tile as in round 1.
+#ifndef MEAO_UPS_PERSIST
+#define MEAO_UPS_PERSIST 1
+#endif
 #ifndef MEAO_UPS_MINB
 #define MEAO_UPS_MINB 5
 #endif
@@ -299,11 +307,19 @@ __device__ __noinline__ void upsample8_slow(const void *hi_depth, int hi_dpitch,
 }  // namespace
 
 cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensorMap &lo_ao_map, const CUtensorMap *lo_ao2_map, bool use_tma,
-                                 const UpsampleArgs &a, const uint8_t *lo_ao2, int lo_a2pitch, cudaStream_t s)
+                                 const UpsampleArgs &a_in, const uint8_t *lo_ao2, int lo_a2pitch, cudaStream_t s)
 {
-    if (a.row1 <= a.row0) return cudaSuccess;
+    if (a_in.row1 <= a_in.row0) return cudaSuccess;
+    UpsampleArgs a = a_in;
     const int ybase = a.row0 & ~1;
-    dim3 grid(ceil_div(a.hiw, kHW), ceil_div(a.row1 - ybase, kHH));
+    a.tiles_x = ceil_div(a.hiw, kHW); a.tiles_y = ceil_div(a.row1 - ybase, kHH);
+    const int ntiles = a.tiles_x * a.tiles_y;
+#if MEAO_UPS_PERSIST
+    if (!a.tile_ctr) return cudaErrorInvalidValue;
+    dim3 grid(min(ntiles, 148 * MEAO_UPS_MINB));     // one wave; the CTAs pull tiles from a.tile_ctr
+#else
+    dim3 grid(ntiles);
+#endif
     const int t = use_tma ? 1 : 0;
     if (!lo_ao2) {
         if (a.hi_ao) {

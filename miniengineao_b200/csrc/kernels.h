@@ -121,6 +121,8 @@ struct UpsampleArgs {
     int fast_div_ok;        // upsample_tolerance and noise_filter_strength are positive normals in [2^-60, 2^60)
                             // (built with MEAO_UPS_STATIC_GUARD: additionally tol >= 2^-55 and 2^-52 <= nfs < 2^59, see blur_upsample.cu)
     int row0, row1;         // output rows (hi level) to produce
+    uint32_t *tile_ctr;     // [0] next tile, [1] CTAs that have run out of tiles: device words owned by (context, level), zero between launches
+    int tiles_x, tiles_y;   // tile grid (filled by launch_blur_upsample)
 };
 // main_premin / main_premin_blendout (COMBINE_LOWER_RESOLUTIONS): the same arguments plus LoResAO2 = HighQuality<lo>
 struct UpsamplePreminArgs { UpsampleArgs base; const uint8_t *lo_ao2; int lo_a2pitch; };

@@ -108,6 +108,7 @@ struct MeaoCtx {
 
     // native neighbour exchange (meao_band_export / _connect / _step)
     BandFlags *band_flags = nullptr;        // first 256 bytes of the arena
+    uint32_t *tile_ctr = nullptr;           // 2 words per upsample level: tile cursor + finished-CTA count of the persistent blur_upsample grid (zero between launches)
     void *peer_base[2] = {nullptr, nullptr};    // the neighbours' arenas through a peer mapping (same layout as ours)
     bool peer_ipc[2] = {false, false};      // mapping came from cudaIpcOpenMemHandle (must be closed)
     unsigned long long band_timeout_ns = 2000000000ull;
@@ -137,6 +138,7 @@ struct MeaoCtx {
     int last_kind = MEAO_DEPTH_RAW_F32;     // ingest kind of the last downsample (selects the atlas padding value)
 
     std::vector<std::pair<std::string, float>> last_profile;
+    int profile_repeats = 1;                // launches per kernel inside one event pair of meao_profile_frame
 };
 
 namespace {
@@ -341,6 +343,7 @@ int allocate(MeaoCtx *c)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     take(sizeof(BandFlags));            // offset 0 in EVERY context's arena (the neighbours address it through their peer mapping)
+    const size_t o_ctr = take(8 * sizeof(uint32_t));
     size_t o_lin = take((size_t)c->lin_pitch * c->lh[0] * sizeof(__half));
     size_t o_res = take((size_t)c->result_pitch * c->lh[0]);
     size_t o_low[5], o_occ[5], o_comb[4], o_hq[5];
@@ -362,6 +365,7 @@ int allocate(MeaoCtx *c)
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     char *b = (char *)c->arena;
     c->band_flags = (BandFlags *)b;
+    c->tile_ctr = (uint32_t *)(b + o_ctr);          // zeroed by the memset above
     {
         BandFlags init{}; init.epoch = 1;
         CUDA_TRY(c, cudaMemcpy(c->band_flags, &init, sizeof init, cudaMemcpyHostToDevice));
@@ -523,6 +527,7 @@ int record_upsample(MeaoCtx *c, int lo, void *ao_out, cudaStream_t s)
 #endif
     }
     a.row0 = c->need_c[hi].lo; a.row1 = c->need_c[hi].hi;
+    a.tile_ctr = c->tile_ctr + 2 * (lo - 1);
     const uint8_t *lo_ao2 = hq_level(c, lo) ? c->hq[lo] : nullptr;                   // kernels main_premin / main_premin_blendout
     CUDA_TRY(c, launch_blur_upsample(c->map_low_ups[lo], single ? c->map_occ1_ups : c->map_ao_ups[lo], &c->map_hq_ups[lo], c->tma_ok, a, lo_ao2, c->occ_pitch[lo], s));
     c->launches++;
@@ -586,20 +591,22 @@ int record_frame(MeaoCtx *c, const void *depth, int kind, void *ao_out, cudaStre
     std::vector<const char *> names;
     std::vector<cudaEvent_t> ev;
     auto mark = [&]() { if (profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back(e); } };
-    int rc;
+    const int reps = profile ? c->profile_repeats : 1;         // every kernel is idempotent (out of place), so repeating it is harmless
+    int rc = 0;
     mark();
-    if ((rc = record_downsample(c, depth, kind, s))) return rc;
+    for (int r = 0; r < reps && !rc; r++) rc = record_downsample(c, depth, kind, s);
+    if (rc) return rc;
     names.push_back("prepare_depth"); mark();
     const int kmax = c->variants.single_scale ? 1 : 4;       // single-scale: Render level 1 + the final-style Upsample only
-    for (int k = 1; k <= kmax; k++) { if ((rc = record_render(c, k, kind, s))) return rc; names.push_back(ren_names[k]); mark(); }
-    for (int k = 1; k <= kmax; k++) if (hq_level(c, k)) { if ((rc = record_render(c, k, kind, s, true))) return rc; names.push_back(hq_names[k]); mark(); }
-    for (int lo = kmax; lo >= 1; lo--) { if ((rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s))) return rc; names.push_back(ups_names[lo]); mark(); }
+    for (int k = 1; k <= kmax; k++) { for (int r = 0; r < reps && !rc; r++) rc = record_render(c, k, kind, s); if (rc) return rc; names.push_back(ren_names[k]); mark(); }
+    for (int k = 1; k <= kmax; k++) if (hq_level(c, k)) { for (int r = 0; r < reps && !rc; r++) rc = record_render(c, k, kind, s, true); if (rc) return rc; names.push_back(hq_names[k]); mark(); }
+    for (int lo = kmax; lo >= 1; lo--) { for (int r = 0; r < reps && !rc; r++) rc = record_upsample(c, lo, lo == 1 ? ao_out : nullptr, s); if (rc) return rc; names.push_back(ups_names[lo]); mark(); }
     if (profile) {
         CUDA_TRY(c, cudaStreamSynchronize(s));
         c->last_profile.clear();
         for (size_t i = 0; i + 1 < ev.size(); i++) {
             float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
-            c->last_profile.push_back({names[i], ms});
+            c->last_profile.push_back({names[i], ms / (float)reps});
         }
         for (auto e : ev) cudaEventDestroy(e);
     }
@@ -1526,6 +1533,13 @@ int meao_selftest_div(MeaoCtx *c, uint64_t n, uint32_t seed, uint64_t *mismatche
     cudaFree(d);
     if (e != cudaSuccess) return fail(c, MEAO_ERR_CUDA, "selftest: %s", cudaGetErrorString(e));
     *mismatches = h;
+    return MEAO_OK;
+}
+
+int meao_set_profile_repeats(MeaoCtx *c, int32_t n)
+{
+    if (!c || n < 1 || n > 1000) return MEAO_ERR_INVALID;
+    c->profile_repeats = n;
     return MEAO_OK;
 }
 

@@ -33,6 +33,7 @@ struct Emu {
     int band0 = 0, band1 = 0, need_lo[5] = {0, 0, 0, 0, 0}, need_hi[5] = {0, 0, 0, 0, 0};
     int ren_tile = -1;      // render tile-height variant (index into kRenderTileHs); -1 = the planner's rule (meao_api.cu render_tile_variant)
     int single_scale = 0;   // MeaoVariants.single_scale
+    uint32_t tile_ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // persistent blur_upsample grid: tile cursor + finished-CTA count per level
     BandFlags flags{};      // native neighbour exchange (band_exchange.cu)
     uint32_t host_error = 0;
 };
@@ -147,6 +148,7 @@ static void run_upsample(Emu *e, int lo)
                     a.noise_filter_strength < 288230376151711744.0f;
 #endif
     a.row0 = e->need_lo[hi]; a.row1 = e->need_hi[hi];
+    a.tile_ctr = e->tile_ctr + 2 * (lo - 1);
     const bool premin = ((e->hq_mask >> (lo - 1)) & 1) != 0;
     const CUtensorMap md = make_map(e->low[lo], 4, e->lw[lo], e->lh[lo], e->low_pitch[lo], kUpsDepthBoxW, kUpsDepthBoxH);
     const CUtensorMap ma = make_map(a.lo_ao, 1, e->lw[lo], e->lh[lo], e->occ_pitch[lo], kUpsAoBoxW, kUpsAoBoxH);

@@ -175,7 +175,7 @@ def test_debug_composite_pass3():
 
 @pytest.mark.parametrize("defs", [
     ("-DMEAO_PACKED_RCP=0",), ("-DMEAO_UPS_V2=0", "-DMEAO_UPS_STATIC_GUARD=1"), ("-DMEAO_UPS_V2=0",), ("-DMEAO_REN_CLAMP_MODE=0",), ("-DMEAO_REN_CLAMP_MODE=2",),
-    ("-DMEAO_UPS_HRUN=2", "-DMEAO_UPS_VRUN=3"), ("-DMEAO_UPS_HRUN=2", "-DMEAO_UPS_VRUN=2"),
+    ("-DMEAO_UPS_HRUN=2", "-DMEAO_UPS_VRUN=3"), ("-DMEAO_UPS_HRUN=2", "-DMEAO_UPS_VRUN=2"), ("-DMEAO_UPS_PERSIST=0",),
 ])
 def test_build_switches_keep_the_arithmetic(defs):
     """Every tuning switch of the kernels (csrc/common.cuh, kernels.h, render_ao.cu) must leave all results unchanged."""
