@@ -47,9 +47,12 @@ constexpr int kBlurW = 34, kBlurH = 18;         // blurred texels needed
 constexpr int kBlurP = 36;                      // pitch of the blurred arrays
 constexpr int kThreads = 256;
 static_assert(kRawH == kUpsDepthBoxH && kRawH == kUpsAoBoxH, "TMA box mismatch");
+constexpr int kBoxDElems = (kRawH * kBoxDP * 4 + 127) / 128 * 128 / 4;      // 3520 B -> 3584 B
+static_assert((kRawH * kBoxAP) % 128 == 0, "the AO box copies must stay 128-byte aligned");
 
 struct __align__(128) Smem {
-    alignas(128) float box_depth[2][kRawH * kBoxDP];    // TMA destination: low-res depth box (LoResDB); two copies: tile i+1 is prefetched while tile i is processed
+    alignas(128) float box_depth[2][kBoxDElems];        // TMA destination: low-res depth box (LoResDB); two copies: tile i+1 is prefetched while tile i is
+                                                        // processed.  Each copy padded to a multiple of 128 bytes: a TMA destination must be 128-byte aligned
     alignas(128) uint8_t box_ao[2][kRawH * kBoxAP];     // TMA destination: low-res AO codes box (LoResAO1)
     alignas(16) float lo_depth[2][kRawH * kLoDP];       // raw low-res depth, column 0 = virtual column lx0 (read until the end of phase 4: double-buffered)
     alignas(16) float inv_depth[kRawH * kRawP];     // DepthCache, UPS:67-71

@@ -99,6 +99,7 @@ inline float rcp_approx(float x) { return (float)(1.0 / (double)x); }
 inline void tma_load_2d(void *dst, const CUtensorMap *m, int x, int y)
 {
     if (((long long)x * m->elem) % 16 != 0) unsupported("TMA start coordinate not 16-byte aligned (faults on B200)");
+    if (((uintptr_t)dst) % 128 != 0) unsupported("TMA shared-memory destination not 128-byte aligned (misaligned-address fault on B200)");
     tma_box_loads++;
     for (int by = 0; by < m->bh; by++)
         for (int bx = 0; bx < m->bw; bx++) {
