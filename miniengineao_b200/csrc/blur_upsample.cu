@@ -25,6 +25,8 @@
 // UPS:23,25,32-34,58-60): a second low-res AO texture (LoResAO2 = HighQuality<lo>, the output of Render.compute
 // kernel `main`) is min-combined with LoResAO1 texel by texel before the blur.  One more u8 TMA box; the min is
 // taken on the unorm8 codes (k -> k/255 is monotone, so it commutes with the load conversion).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -291,7 +293,8 @@ __device__ __noinline__ void upsample8_slow(const void *hi_depth, int hi_dpitch,
 #define MEAO_UPS_VRUN 6         // 6: 51 threads; 3: 102 threads; 2: 153 threads
 #endif
 #ifndef MEAO_UPS_V2_UNROLL
-#define MEAO_UPS_V2_UNROLL 0        // 1: both 4-pixel halves of phase 4 in flight (more ILP, more registers)
+#define MEAO_UPS_V2_UNROLL 1        // 1: both 4-pixel halves of phase 4 in flight (more ILP; 4 bytes spilled at the 48-register cap); measured
+                                    // with the tile loop, final level: 33.1 vs 35.1 us (0 = the rolled loop)
 #endif
 // Persistent tile loop with TMA prefetch of the next tile (see blur_upsample_kernel.inc); 0 = one CTA per tile as in round 1.
 #ifndef MEAO_UPS_PERSIST
@@ -317,12 +320,15 @@ cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensor
     const int ybase = a.row0 & ~1;
     a.tiles_x = ceil_div(a.hiw, kHW); a.tiles_y = ceil_div(a.row1 - ybase, kHH);
     const int ntiles = a.tiles_x * a.tiles_y;
-#if MEAO_UPS_PERSIST
-    if (!a.tile_ctr) return cudaErrorInvalidValue;
-    dim3 grid(min(ntiles, 148 * MEAO_UPS_MINB));     // one wave; the CTAs pull tiles from a.tile_ctr
-#else
-    dim3 grid(ntiles);
-#endif
+    // The tile loop pays when a CTA gets several tiles (the final level of a 4K frame: 5.5): the next tile's boxes are prefetched and
+    // the launch ramp is paid once.  With ~1-2 tiles per CTA it loses (measured: 1020 tiles, 15.8 vs 14.7 us; 255 tiles, 8.4 vs 6.5 us):
+    // the atomic fetch + staging sit on a short critical path and a 2-vs-1 split of tiles is the worst possible tail.
+    constexpr int kWave = 148 * MEAO_UPS_MINB;
+    const char *force = getenv("MEAO_UPS_PERSIST_MIN_WAVES");       // tuning aid: tiles / wave from which the loop is used (default 2)
+    const double min_waves = force ? atof(force) : 2.0;
+    const bool persist = MEAO_UPS_PERSIST && a.tile_ctr && ntiles >= (int)(min_waves * kWave);
+    if (!persist) a.tile_ctr = nullptr;
+    dim3 grid(persist ? kWave : ntiles);
     const int t = use_tma ? 1 : 0;
     if (!lo_ao2) {
         if (a.hi_ao) {
