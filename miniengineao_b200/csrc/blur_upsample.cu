@@ -61,7 +61,7 @@ struct __align__(128) Smem {
     alignas(16) float ao[kRawH * kRawP];            // AOCache1 as loaded, UPS:62-65
     alignas(16) float hblur[kRawH * kBlurP];        // AOCache2, UPS:127-129
     alignas(16) float vblur[kBlurH * kBlurP];       // AOCache1 after the vertical pass, UPS:168-169
-    alignas(8) uint64_t bar[2];
+    struct alignas(16) Bar { uint64_t v; uint64_t pad_; } bar_[2];     // one mbarrier per box-buffer pair, each in its own 16-byte slot
     alignas(16) int4 tile[2];                       // this / the next iteration's tile, decoded by thread 0: hx0 (-1 = none), hy0, interior
 };
 struct SmemPremin : Smem {
