@@ -694,7 +694,7 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true", help="skip every CPU-oracle leg (cpu_baseline, oracle checks)")
     ap.add_argument("--quick", action="store_true", help="headline + e2e + roofline only (skip the other configs and the composite)")
     ap.add_argument("--streams", type=int, default=5, help="contexts/streams that frames alternate over in throughput mode")
-    ap.add_argument("--band-streams", type=int, default=8, help="band contexts per rank in the row-tiled 8K measurement")
+    ap.add_argument("--band-streams", type=int, default=12, help="band contexts per rank in the row-tiled 8K measurement")
     ap.add_argument("--only-8k", action="store_true", help="development aid: only the 8K single-frame / row-band measurement")
     ap.add_argument("--band-mode", default="native", choices=["native", "p2p"], help="halo exchange: peer stores inside the graph / NCCL send-recv between two graphs")
     args = ap.parse_args()
