@@ -92,11 +92,24 @@ class RowTiledAO:
         allh = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(allh, mine, group=self.group)
         handles = [bytes(h.cpu().numpy().tobytes()) for h in allh]
-        if self.rank > 0:
-            self.ao.band_connect(0, handles[self.rank - 1])
-        if self.rank + 1 < self.world:
-            self.ao.band_connect(1, handles[self.rank + 1])
-        dist.barrier(group=self.group)      # nobody steps before every mapping exists
+        err = None
+        try:
+            if self.rank > 0:
+                self.ao.band_connect(0, handles[self.rank - 1])
+            if self.rank + 1 < self.world:
+                self.ao.band_connect(1, handles[self.rank + 1])
+        except Exception as e:              # no peer access / IPC on this box
+            err = e
+        # the decision must be COLLECTIVE: a rank that fell back while its neighbours stepped natively would leave them spinning
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev if backend == "nccl" else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)       # also: nobody steps before every mapping exists
+        if int(ok.item()) == 0:
+            for side in (0, 1):
+                try:
+                    self.ao.band_connect(side, None)
+                except Exception:
+                    pass
+            raise RuntimeError(f"native neighbour exchange unavailable on at least one rank ({err if err else 'another rank failed'})")
 
     @property
     def rows(self) -> int:

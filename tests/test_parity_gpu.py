@@ -1015,3 +1015,31 @@ def test_pure_c_client_drives_row_bands(torch_cuda, tmp_path):
     for nb, nd in ((2, 1), (3, 1), (2, ndev)):
         r = subprocess.run([exe, "bands", str(W), str(H), dpath, apath, "1.1", str(nb), str(nd)], capture_output=True, text=True, env=env, timeout=120)
         assert r.returncode == 0 and " 0 mismatching pixels" in r.stdout, r.stdout + r.stderr
+
+
+def test_bad_depth_kind_is_refused_by_every_entry_point(torch_cuda):
+    """only meao_render validated depth_kind; the check now sits in the downsample recorder all entry points share."""
+    from miniengineao_b200 import AmbientOcclusion, Camera, rowtile
+    from miniengineao_b200 import _native as N
+    torch = torch_cuda
+    W, H = 640, 736
+    lib = N.lib()
+    ao = AmbientOcclusion(Camera(W, H), device=0)
+    ao.LateUpdate()
+    d = torch.zeros((H, W), dtype=torch.float32, device="cuda")
+    o = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.meao_render(ao._ctx, d.data_ptr(), 7, o.data_ptr(), st) == N.MEAO_ERR_INVALID
+    assert lib.meao_stage_downsample(ao._ctx, d.data_ptr(), -1, st) == N.MEAO_ERR_INVALID
+    assert lib.meao_render_band_prepare(ao._ctx, d.data_ptr(), 4, st) == N.MEAO_ERR_INVALID
+    cuts = rowtile.partition(H, 2)
+    ao.set_row_band(cuts[0], cuts[1], *rowtile.neighbours(cuts, 0))
+    send = torch.zeros(int(ao.halo_bytes(1)), dtype=torch.uint8, device="cuda")
+    assert lib.meao_band_phase_a(ao._ctx, d.data_ptr(), 9, None, send.data_ptr(), st) == N.MEAO_ERR_INVALID
+    hp = lib.meao_host_alloc(W * H * 4)
+    try:
+        assert lib.meao_render_host_async(ao._ctx, hp, 5, hp, 0) == N.MEAO_ERR_INVALID
+    finally:
+        lib.meao_host_free(hp)
+    torch.cuda.synchronize()
+    assert b"bad depth kind" in lib.meao_last_error(ao._ctx)
