@@ -45,7 +45,7 @@ template <int MODE, int TH> struct Geo {
     static constexpr int kSH = TH + 2 * kAp;        // == render_box_h(TH, MODE == 1)
 };
 #ifndef MEAO_REN_MINB
-#define MEAO_REN_MINB 5
+#define MEAO_REN_MINB 6
 #endif
 constexpr int kThreads = MEAO_REN_THREADS;
 constexpr int kWarps = kThreads / 32;
