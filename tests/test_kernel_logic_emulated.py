@@ -290,3 +290,21 @@ def test_native_exchange_times_out_instead_of_hanging():
 def test_tolerances_outside_the_proven_range_take_the_ieee_path():
     """fast_div_ok = 0 (upsample tolerance 10^-17 < 2^-55): the whole upsample runs upsample8_slow."""
     _run(161, 93, seed=21, upsample_tolerance=-17.0, noise_filter_tolerance=-8.0, intensity=1.2)
+
+
+@pytest.mark.parametrize("use_tma", [True, False])
+def test_persistent_tile_loop_forced_on_every_level(use_tma, monkeypatch):
+    """The tile loop of blur_upsample (atomic tile cursor, next tile's boxes staged into the other buffer pair, per-barrier wait parity,
+    double-buffered lo_depth, counters re-armed by the last CTA) is used on the GPU only when a launch has >= 2 tiles per CTA slot;
+    MEAO_UPS_PERSIST_MIN_WAVES forces it everywhere.  In the fiber emulator the first CTA then walks ALL tiles of a level, interior
+    and border tiles mixed, and the second frame must find the counters re-armed."""
+    monkeypatch.setenv("MEAO_UPS_PERSIST_MIN_WAVES", "0.0001")
+    W, H = 640, 360
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    depth[100:130, 200:300] = 0.0                                   # sky: the out-of-line IEEE path inside the loop
+    orc = Oracle(W, H, threads=4, intensity=1.1, high_quality_mask=0b0101)
+    ref = orc.run(depth)
+    f = EmulatedFrame(_plan(W, H, intensity=1.1, high_quality_mask=0b0101), use_tma=use_tma)
+    for frame in range(2):
+        assert np.array_equal(f.run(depth), ref), frame
+    _compare_all(f, orc, "tile loop", 0b0101)

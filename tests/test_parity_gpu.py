@@ -1043,3 +1043,22 @@ def test_bad_depth_kind_is_refused_by_every_entry_point(torch_cuda):
         lib.meao_host_free(hp)
     torch.cuda.synchronize()
     assert b"bad depth kind" in lib.meao_last_error(ao._ctx)
+
+
+def test_persistent_tile_loop_forced_on_every_level(torch_cuda, monkeypatch):
+    """blur_upsample's tile loop (one wave of CTAs pulling tiles from an atomic cursor, the next tile's TMA boxes prefetched into a
+    second buffer pair) normally serves only launches with >= 2 tiles per CTA slot (the final level from 4K up -- covered by the 4K /
+    8K tests); MEAO_UPS_PERSIST_MIN_WAVES forces it onto every level, where a CTA's tile sequence mixes interior and border tiles
+    and most CTAs find the cursor exhausted at once.  Three frames: the counters must be re-armed by the last CTA each time."""
+    from miniengineao_b200 import synth
+    torch = torch_cuda
+    monkeypatch.setenv("MEAO_UPS_PERSIST_MIN_WAVES", "0.0001")
+    W, H = 1280, 720
+    ao, orc = _mk(W, H, intensity=1.1, high_quality_mask=0b0101)
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    depth[300:340, 500:700] = 0.0
+    ref = orc.run(depth)
+    d = torch.from_numpy(depth).cuda()
+    for frame in range(3):
+        assert np.array_equal(ao.render(d).cpu().numpy(), ref), frame
+    _compare_all(ao, orc, "forced tile loop", extra=[18, 20])
