@@ -265,7 +265,10 @@ int meao_band_phase_b(MeaoCtx *ctx, const void *recv_up_dev, const void *recv_do
 typedef struct { unsigned char bytes[MEAO_PEER_HANDLE_BYTES]; } MeaoPeerHandle;
 int meao_band_export(MeaoCtx *ctx, MeaoPeerHandle *out);
 /* peer == NULL disconnects that side.  Same process: direct pointer (+ cudaDeviceEnablePeerAccess across devices);
- * another process: cudaIpcOpenMemHandle.  Fails with MEAO_ERR_INVALID if the neighbour's frame size differs. */
+ * another process: cudaIpcOpenMemHandle.  Fails with MEAO_ERR_INVALID if the neighbour's frame size differs.
+ * The bands' epoch counters run in lock step from 1, so a band that has already stepped can only be reconnected as a whole:
+ * disconnect both of its sides (and do the same on every other band of the frame), then connect again -- the first connect of a
+ * fully disconnected band restarts its epoch and clears a sticky time-out error. */
 int meao_band_connect(MeaoCtx *ctx, int32_t side, const MeaoPeerHandle *peer);
 int meao_band_step(MeaoCtx *ctx, const void *depth_band_dev, int32_t depth_kind, void *ao_band_out_dev, void *stream);
 /* The same with HOST buffers (the band's rows only): H2D copy, the step, D2H copy, all enqueued on the context's staging slot 0 --

@@ -1080,6 +1080,18 @@ int meao_band_connect(MeaoCtx *c, int32_t side, const MeaoPeerHandle *peer)
     c->peer_base[side] = nullptr; c->peer_ipc[side] = false;
     if (!peer) return MEAO_OK;
     if ((side == 0 && c->prev0 < 0) || (side == 1 && c->next1 < 0)) return fail(c, MEAO_ERR_INVALID, "this band has no neighbour on side %d", side);
+    {   // The epoch counters of neighbouring bands advance in lock step from 1.  A context that has already stepped can only be
+        // (re)connected as a whole: with the other side still attached its epoch cannot restart, and the new neighbour starts at 1.
+        BandFlags f{};
+        CUDA_TRY(c, cudaMemcpy(&f, c->band_flags, sizeof f, cudaMemcpyDeviceToHost));
+        if (f.epoch != 1 || f.error != 0) {
+            if (c->peer_base[side ^ 1])
+                return fail(c, MEAO_ERR_INVALID, "this band has stepped (epoch %u): disconnect BOTH sides, then connect them again -- every band of the frame restarts at epoch 1", f.epoch);
+            BandFlags init{}; init.epoch = 1;
+            CUDA_TRY(c, cudaMemcpy(c->band_flags, &init, sizeof init, cudaMemcpyHostToDevice));
+            if (c->host_error) *c->host_error = 0;
+        }
+    }
     PeerHandlePod h;
     memcpy(&h, peer->bytes, sizeof h);
     if (h.magic != kPeerMagic) return fail(c, MEAO_ERR_INVALID, "not a MeaoPeerHandle");

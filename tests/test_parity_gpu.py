@@ -1062,3 +1062,45 @@ def test_persistent_tile_loop_forced_on_every_level(torch_cuda, monkeypatch):
     for frame in range(3):
         assert np.array_equal(ao.render(d).cpu().numpy(), ref), frame
     _compare_all(ao, orc, "forced tile loop", extra=[18, 20])
+
+
+def test_native_exchange_reconnect_restarts_the_epochs(torch_cuda):
+    """Bands that have stepped can be taken apart and connected again (e.g. after one of them timed out): partial reconnects are
+    refused, a full disconnect + connect restarts every epoch at 1 and the frames are right again."""
+    from miniengineao_b200 import MeaoError, synth
+    from miniengineao_b200 import _native as N
+    from oracle.oracle import Oracle
+    torch = torch_cuda
+    W, H, bands = 1280, 1200, 3
+    cuts, ctxs, streams = _native_bands(torch, W, H, bands, intensity=1.1)
+    depth = synth.lin01_to_raw(synth.corridor(W, H))
+    ref = Oracle(W, H, threads=8, intensity=1.1).run(depth)
+    outs = [torch.zeros((cuts[i + 1] - cuts[i], W), dtype=torch.uint8, device="cuda") for i in range(bands)]
+    bufs = [torch.from_numpy(depth[cuts[i]:cuts[i + 1]]).cuda() for i in range(bands)]
+
+    def frame():
+        for o in outs:
+            o.zero_()
+        for i, a in enumerate(ctxs):
+            a.band_step(bufs[i], outs[i], stream=streams[i])
+        torch.cuda.synchronize()
+        return np.concatenate([o.cpu().numpy() for o in outs], axis=0)
+    for _ in range(2):
+        assert np.array_equal(frame(), ref)
+    assert ctxs[1].band_status()["epoch"] == 3
+    handles = [a.band_export() for a in ctxs]
+    with pytest.raises(MeaoError) as e:                          # the middle band has stepped and its lower side is still attached
+        ctxs[1].band_connect(0, handles[0])
+    assert e.value.code == N.MEAO_ERR_INVALID
+    for i, a in enumerate(ctxs):                                 # take everything apart ...
+        for side in (0, 1):
+            a.band_connect(side, None)
+    for i, a in enumerate(ctxs):                                 # ... and connect again: epochs restart at 1 everywhere
+        if i > 0:
+            a.band_connect(0, handles[i - 1])
+        if i + 1 < bands:
+            a.band_connect(1, handles[i + 1])
+    assert [a.band_status()["epoch"] for a in ctxs] == [1, 1, 1]
+    for _ in range(2):
+        assert np.array_equal(frame(), ref)
+    assert [a.band_status()["error"] for a in ctxs] == [0, 0, 0]
