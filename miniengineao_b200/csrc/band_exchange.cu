@@ -98,4 +98,8 @@ cudaError_t launch_band_exchange(const XchgArgs &a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+#ifndef MEAO_EMULATE
+cudaError_t preload_band_exchange_kernel() { return preload_kernel(band_exchange_kernel); }
+#endif
+
 }  // namespace meao

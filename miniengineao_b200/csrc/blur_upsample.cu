@@ -352,4 +352,16 @@ cudaError_t launch_blur_upsample(const CUtensorMap &lo_depth_map, const CUtensor
     return cudaGetLastError();
 }
 
+#ifndef MEAO_EMULATE
+cudaError_t preload_blur_upsample()
+{
+    cudaError_t e = cudaSuccess;
+    auto t = [&](auto k) { if (e == cudaSuccess) e = preload_kernel(k); };
+    t(blur_upsample_kernel<true, true>); t(blur_upsample_kernel<true, false>); t(blur_upsample_kernel<false, true>); t(blur_upsample_kernel<false, false>);
+    t(blur_upsample_premin_kernel<true, true>); t(blur_upsample_premin_kernel<true, false>);
+    t(blur_upsample_premin_kernel<false, true>); t(blur_upsample_premin_kernel<false, false>);
+    return e;
+}
+#endif
+
 }  // namespace meao

@@ -97,4 +97,12 @@ cudaError_t launch_composite(const uint8_t *ao, void *color, long long npix, int
     return cudaGetLastError();
 }
 
+#ifndef MEAO_EMULATE
+cudaError_t preload_composite_kernels()
+{
+    const cudaError_t e = preload_kernel(composite_kernel<false>);
+    return e != cudaSuccess ? e : preload_kernel(composite_kernel<true>);
+}
+#endif
+
 }  // namespace meao

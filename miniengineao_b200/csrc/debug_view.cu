@@ -88,4 +88,18 @@ cudaError_t launch_debug_view(const DebugViewArgs &a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+#ifndef MEAO_EMULATE
+cudaError_t preload_composite_kernels();
+cudaError_t preload_selftest_kernel();
+cudaError_t preload_aux_kernels()
+{
+    cudaError_t e = preload_kernel(debug_view_kernel);
+    if (e == cudaSuccess) e = preload_kernel(debug_composite_kernel<false>);
+    if (e == cudaSuccess) e = preload_kernel(debug_composite_kernel<true>);
+    if (e == cudaSuccess) e = preload_composite_kernels();
+    if (e == cudaSuccess) e = preload_selftest_kernel();
+    return e;
+}
+#endif
+
 }  // namespace meao

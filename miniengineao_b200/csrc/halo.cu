@@ -34,4 +34,13 @@ cudaError_t launch_halo_copy(const HaloArgs &a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+#ifndef MEAO_EMULATE
+cudaError_t preload_band_exchange_kernel();
+cudaError_t preload_band_kernels()
+{
+    const cudaError_t e = preload_kernel(halo_copy_kernel);
+    return e != cudaSuccess ? e : preload_band_exchange_kernel();
+}
+#endif
+
 }  // namespace meao

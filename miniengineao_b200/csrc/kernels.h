@@ -181,6 +181,20 @@ struct XchgArgs {
 };
 cudaError_t launch_band_exchange(const XchgArgs &a, cudaStream_t s);
 
+// ---- eager loading ------------------------------------------------------------------------------------------------------
+// CUDA loads kernels lazily, on first launch, and that load can wait for kernels already RUNNING on the device.  A band's exchange
+// kernel spins until its neighbour has run -- if the neighbour's first launch then has to load a kernel on the same device, the two
+// wait for each other until the exchange times out (seen when the band tests ran first in a fresh process).  meao_create therefore
+// touches every kernel of the library once per device (cudaFuncGetAttributes forces the load).
+#ifndef MEAO_EMULATE
+template <class K> inline cudaError_t preload_kernel(K kernel) { cudaFuncAttributes at; return cudaFuncGetAttributes(&at, (const void *)kernel); }
+cudaError_t preload_prepare_depth();
+cudaError_t preload_render_ao();
+cudaError_t preload_blur_upsample();
+cudaError_t preload_band_kernels();
+cudaError_t preload_aux_kernels();      // composite, debug views, self test
+#endif
+
 // ---- halo pack / unpack: row blocks of pitched buffers <-> contiguous staging, one launch ------
 struct HaloSeg { const float *src; float *dst; int src_pitch, dst_pitch, width, rows; };
 struct HaloArgs { HaloSeg seg[8]; int nseg; };

@@ -708,6 +708,21 @@ int meao_create(const MeaoDeviceCfg *cfg, MeaoCtx **out)
         if (cudaHostGetDevicePointer((void **)&c->host_error_dev, c->host_error, 0) != cudaSuccess) c->host_error_dev = nullptr;
     } else c->host_error = nullptr;
     cudaGetLastError();
+    {   // load every kernel of the library on this device NOW (kernels.h "eager loading"): a lazy load later could wait for a
+        // spinning exchange kernel that in turn waits for the very launch that triggered the load
+        static std::mutex preload_mutex;
+        static std::map<int, bool> preloaded;
+        std::lock_guard<std::mutex> g(preload_mutex);
+        if (!preloaded[dev]) {
+            cudaError_t pe = preload_prepare_depth();
+            if (pe == cudaSuccess) pe = preload_render_ao();
+            if (pe == cudaSuccess) pe = preload_blur_upsample();
+            if (pe == cudaSuccess) pe = preload_band_kernels();
+            if (pe == cudaSuccess) pe = preload_aux_kernels();
+            if (pe != cudaSuccess) { cudaGetLastError(); meao_destroy(c); return fail(nullptr, MEAO_ERR_CUDA, "loading the kernels failed: %s", cudaGetErrorString(pe)); }
+            preloaded[dev] = true;
+        }
+    }
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     const char *no_tma = getenv("MEAO_DISABLE_TMA");     // debugging aid: force the gather path in every tile

@@ -205,4 +205,17 @@ cudaError_t launch_prepare_depth(const PrepareArgs &a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+#ifndef MEAO_EMULATE
+cudaError_t preload_prepare_depth()
+{
+    cudaError_t e = cudaSuccess;
+    auto t = [&](auto k) { if (e == cudaSuccess) e = preload_kernel(k); };
+    t(prepare_depth_kernel<false, true, IN_F32>);
+    t(prepare_depth_kernel<true, true, IN_F32>); t(prepare_depth_kernel<true, false, IN_F32>);
+    t(prepare_depth_kernel<true, true, IN_D16>); t(prepare_depth_kernel<true, false, IN_D16>);
+    t(prepare_depth_kernel<true, true, IN_D24S8>); t(prepare_depth_kernel<true, false, IN_D24S8>);
+    return e;
+}
+#endif
+
 }  // namespace meao

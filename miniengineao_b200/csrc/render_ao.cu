@@ -302,4 +302,18 @@ cudaError_t launch_synth_tiled(const float *low, int lw, int lh, int lpitch, int
     return cudaGetLastError();
 }
 
+#ifndef MEAO_EMULATE
+cudaError_t preload_render_ao()
+{
+    cudaError_t e = cudaSuccess;
+    auto t = [&](auto k) { if (e == cudaSuccess) e = preload_kernel(k); };
+    t(render_ao_kernel<0, false, 32>); t(render_ao_kernel<0, false, 16>); t(render_ao_kernel<0, false, 8>);
+    t(render_ao_kernel<0, true, 32>); t(render_ao_kernel<0, true, 16>); t(render_ao_kernel<0, true, 8>);
+    t(render_ao_kernel<1, false, 32>); t(render_ao_kernel<1, false, 16>); t(render_ao_kernel<1, false, 8>);
+    t(render_ao_kernel<1, true, 32>); t(render_ao_kernel<1, true, 16>); t(render_ao_kernel<1, true, 8>);
+    t(synth_tiled_kernel);
+    return e;
+}
+#endif
+
 }  // namespace meao

@@ -58,4 +58,8 @@ cudaError_t launch_selftest_div(uint64_t n, uint32_t seed, unsigned long long *m
     return cudaGetLastError();
 }
 
+#ifndef MEAO_EMULATE
+cudaError_t preload_selftest_kernel() { return preload_kernel(selftest_div_kernel); }
+#endif
+
 }  // namespace meao
