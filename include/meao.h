@@ -259,8 +259,8 @@ int meao_band_phase_b(MeaoCtx *ctx, const void *recv_up_dev, const void *recv_do
  * while it waits.  With one band per GPU that is automatic as long as every host issues the steps of its band contexts in the same
  * order (frame streams over several contexts per GPU are fine: bench.py runs 12).  When NEIGHBOURING bands share one GPU (tests,
  * single-GPU development) every band's streams need their own hardware queue: set CUDA_DEVICE_MAX_CONNECTIONS=32 before CUDA starts
- * and keep to <= 4 bands per GPU -- otherwise a band's kernels can be queued behind the spinning kernel that waits for them, which the
- * time-out then reports as error 1 / 2. */
+ * and keep to <= 3 bands per GPU -- otherwise a band's kernels (or its first graph instantiation) can end up waiting behind the
+ * spinning kernel that waits for them, which the time-out then reports as error 1 / 2. */
 #define MEAO_PEER_HANDLE_BYTES 128
 typedef struct { unsigned char bytes[MEAO_PEER_HANDLE_BYTES]; } MeaoPeerHandle;
 int meao_band_export(MeaoCtx *ctx, MeaoPeerHandle *out);
