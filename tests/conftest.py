@@ -14,6 +14,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "run_last: collected after every other test (several spinning band contexts on ONE GPU: a "
+                            "scheduling hazard of that arrangement must not stop a -x run before the other parity tests have reported)")
 
 
 def _have_gpu() -> bool:
@@ -26,6 +28,7 @@ def _have_gpu() -> bool:
 
 def pytest_collection_modifyitems(config, items):
     """`gpu`-marked tests are SKIPPED (not failed) on a box without a GPU, so a plain `pytest tests/` is green on CPU."""
+    items.sort(key=lambda it: 1 if "run_last" in it.keywords else 0)      # stable: everything else keeps its order
     if _have_gpu():
         return
     skip = pytest.mark.skip(reason="needs a B200 (no CUDA device visible); run with -m gpu on the GPU box")
