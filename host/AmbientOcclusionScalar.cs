@@ -47,6 +47,7 @@ namespace MiniEngineAO.ScalarCpu
         public AoParams p = AoParams.Default();
         public AoCamera cam = new AoCamera { nearClip = 0.3f, farClip = 100f, tanHalfFovH = 1f, reversedZ = true };
         public int threads = 1;
+        public bool singleScale;        // BASELINE.json configs[0]: Downsample1 -> Render level 1 -> the final-style Upsample fed with Occlusion1
 
         // post-quantisation values: an f16 buffer holds floats representable in f16, a UNORM8 buffer holds k * (1/255)
         public float[] linearDepth;                         // id 1       L0      f16
@@ -390,7 +391,7 @@ namespace MiniEngineAO.ScalarCpu
         public void Upsample(int lo)                        // meao_oracle_upsample, wiring AmbientOcclusion.cs:528-531
         {
             int hi = lo - 1, low = lw[lo], loh = lh[lo], hiw = lw[hi], hih = lh[hi];
-            float[] loDepth = lowDepth[lo], loAo = (lo == 4) ? occlusion[4] : combined[lo];
+            float[] loDepth = lowDepth[lo], loAo = (lo == 4 || (singleScale && lo == 1)) ? occlusion[lo] : combined[lo];   // meao_oracle.c: single_scale
             float[] hiDepth = (hi == 0) ? linearDepth : lowDepth[hi], hiAo = (hi == 0) ? null : occlusion[hi];
             float[] dest = (hi == 0) ? result : combined[hi];
             float nfs, S, kB, tol;
@@ -437,8 +438,9 @@ namespace MiniEngineAO.ScalarCpu
         public byte[] Run(float[] depth)                    // meao_oracle_run, record order AmbientOcclusion.cs:511-531
         {
             Downsample(depth);
-            for (int k = 1; k <= 4; k++) Render(k);
-            for (int lo = 4; lo >= 1; lo--) Upsample(lo);
+            int kmax = singleScale ? 1 : 4;                 // single-scale: nothing coarser than level 1 contributes
+            for (int k = 1; k <= kmax; k++) Render(k);
+            for (int lo = kmax; lo >= 1; lo--) Upsample(lo);
             byte[] ao = new byte[W * H];
             for (int i = 0; i < ao.Length; i++) ao[i] = (byte)(uint)((float)(result[i] * 255.0f) + 0.5f);
             return ao;

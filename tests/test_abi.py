@@ -251,6 +251,7 @@ def test_csharp_scalar_twin_names_every_oracle_stage():
     for method in ("Downsample", "Render", "Upsample", "Run", "TimeFrames", "Unorm8Code", "SampleThickness"):
         assert re.search(r"\b" + method + r"\s*\(", cs), method
     assert "(GI & 9) == 0" in cs            # Downsample1.compute:73 uses the OCTAL literal 011
+    assert re.search(r"singleScale\s*&&\s*lo\s*==\s*1", cs)      # BASELINE configs[0]: the oracle's single_scale rule (Occlusion1 as LoResAO1)
 
 
 # ---- round 2: ABI 3 -----------------------------------------------------------------------------------------------------------
